@@ -1,0 +1,81 @@
+// common.cuh — shared device/host helpers for libcris_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../../include/cris_b200.h"
+
+namespace cris {
+
+// ---- host-side error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define CRIS_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::cris::set_error(__VA_ARGS__);        \
+      return -1;                             \
+    }                                        \
+  } while (0)
+
+#define CRIS_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::cris::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                      \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+#define CRIS_LAUNCH_OK()                                                                \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::cris::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),     \
+                        __FILE__, __LINE__);                                            \
+      return -3;                                                                        \
+    }                                                                                   \
+    ::cris::count_launch();                                                             \
+  } while (0)
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// padded-NHWC row -> is it an interior pixel?
+__device__ __forceinline__ bool interior_row(long long r, int hp, int wp) {
+  if (wp <= 0) return true;
+  int rr = (int)(r % ((long long)hp * wp));
+  int h = rr / wp, w = rr - h * wp;
+  return (h >= 1) && (h <= hp - 2) && (w >= 1) && (w <= wp - 2);
+}
+
+}  // namespace cris
