@@ -21,7 +21,7 @@ ARCHS = {
     "r101": dict(layers=(3, 4, 23, 3), embed_dim=512, width=64, twidth=512, tlayers=12, vocab=49408, ctx=77,
                  spacial=7),
     # reduced-width variant for fast CPU tests (same topology / code paths, ~1/16 the FLOPs)
-    "tiny": dict(layers=(1, 2, 1, 1), embed_dim=128, width=16, twidth=64, tlayers=2, vocab=512, ctx=77,
+    "tiny": dict(layers=(1, 2, 1, 1), embed_dim=128, width=16, twidth=128, tlayers=2, vocab=512, ctx=77,
                  spacial=7),
 }
 
