@@ -1,0 +1,142 @@
+"""ctypes binding of libcris_b200.so (the C ABI declared in include/cris_b200.h).
+
+The product path has NO fallback: if the library cannot be loaded, or a call fails, a RuntimeError is
+raised (the reference's error convention is Python exceptions, e.g. model/layers.py:113-115).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libcris_b200.so"
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `cris_gemm_args` (include/cris_b200.h)."""
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64), ("strideA", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("strideB", C.c_int64),
+        ("D", C.c_void_p), ("ldd", C.c_int64), ("strideD", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("batch", C.c_int32),
+        ("a_mn", C.c_int32), ("b_mn", C.c_int32),
+        ("d_fp32", C.c_int32), ("accumulate", C.c_int32),
+        ("tap_mode", C.c_int32), ("taps", C.c_int32),
+        ("tap_off", C.c_int32 * 9),
+        ("b_tap_k", C.c_int32), ("b_tap_n", C.c_int32), ("d_tap_n", C.c_int32),
+        ("splits", C.c_int32),
+        ("alpha", C.c_float),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("resid", C.c_void_p), ("ldr", C.c_int64), ("strideR", C.c_int64), ("resid_fp32", C.c_int32),
+        ("mask_hp", C.c_int32), ("mask_wp", C.c_int32),
+        ("colstats", C.c_void_p),
+        ("a_rows", C.c_int32), ("b_rows", C.c_int32),
+        ("batch_inner", C.c_int32),
+        ("strideA2", C.c_int64), ("strideB2", C.c_int64), ("strideD2", C.c_int64), ("strideR2", C.c_int64),
+        ("d_col_stride", C.c_int32),
+    ]
+
+
+# signature mini-language: p = pointer, q = int64, i = int32, f = float, d = double, u = uint64
+_T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "d": C.c_double, "u": C.c_uint64}
+_SIGS = {
+    "cris_col_reduce": "ipqipqpqpqippqiiiipip",
+    "cris_bn_reduce_partials": "piipp",
+    "cris_bn_coeffs": "pdppffppppppiip",
+    "cris_bn_apply": "pqpppqpqqiiiip",
+    "cris_bn_bwd_apply": "pqpqpqppppdpqpqiqiiiip",
+    "cris_layernorm_fwd": "piqpppqipiqpqppqifp",
+    "cris_layernorm_bwd": "piqpqpiqppppiqiqip",
+    "cris_avgpool2_fwd": "pqpqiiiip",
+    "cris_avgpool2_bwd": "pqpqiiiiip",
+    "cris_upsample2x_fwd": "pqpqiiiip",
+    "cris_upsample2x_bwd": "pqpqiiiiip",
+    "cris_mul_bcast": "pqpqpqqiip",
+    "cris_mul_bcast_bwd_s": "pqpqpiiip",
+    "cris_padded_to_tokens": "pqpqpiqiiiip",
+    "cris_tokens_to_padded": "piqpqiiiip",
+    "cris_coord_fill": "pqiiiip",
+    "cris_stem_conv1_fwd": "pppqiiiip",
+    "cris_stem_conv1_wgrad": "ppqpiiiip",
+    "cris_softmax_fwd": "pppqqiiiipifup",
+    "cris_softmax_bwd": "ppqqiiifup",
+    "cris_embed_fwd": "ppppiiip",
+    "cris_embed_bwd": "ppppiiip",
+    "cris_eot_gather": "ppiqpqiiip",
+    "cris_eot_scatter": "ppiqpiqiiip",
+    "cris_elementwise": "ipiqpiqpiqqifup",
+    "cris_pack_conv_weight": "ppiiiip",
+    "cris_pack_matrix": "ppqiip",
+    "cris_batch_reduce": "piqpqiiiip",
+    "cris_small_matmul": "pppiiiiip",
+    "cris_dynconv_bce_fwd": "pqpqpiipppiiiip",
+    "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m cris.pytorch_b200.build` "
+                "(cris.pytorch_b200 has no CPU / eager fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.cris_last_error.restype = C.c_char_p
+        L.cris_launch_count.restype = C.c_uint64
+        L.cris_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+        L.cris_gemm.restype = C.c_int
+        L.cris_set_gemm_impl.argtypes = [C.c_int]
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_T[ch] for ch in sig]
+            fn.restype = C.c_int
+        if L.cris_gemm_args_size() != C.sizeof(GemmArgs) or \
+                L.cris_gemm_args_last_offset() != GemmArgs.d_col_stride.offset:
+            raise RuntimeError("cris_gemm_args layout mismatch between include/cris_b200.h and _lib.GemmArgs")
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    """Every entry point include/cris_b200.h declares (used by the CPU 'library loads' test)."""
+    return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
+            "cris_launch_count", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"libcris_b200 {what} failed: {lib().cris_last_error().decode()}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an entry point on the current CUDA stream (appended as the last argument)."""
+    rc = getattr(lib(), name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"libcris_b200 {name} failed: {lib().cris_last_error().decode()}")
+
+
+def gemm(args: GemmArgs):
+    rc = lib().cris_gemm(C.byref(args), stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"libcris_b200 cris_gemm failed: {lib().cris_last_error().decode()}")
+
+
+def device_check():
+    rc = lib().cris_device_check()
+    if rc != 0:
+        raise RuntimeError(f"libcris_b200: {lib().cris_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().cris_launch_count())

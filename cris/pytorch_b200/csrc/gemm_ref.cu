@@ -26,8 +26,10 @@ __global__ void gemm_ref_kernel(const RefArgs r) {
   const int ztap = z % taps_z;
   const int batch = z / taps_z;
   if (m >= a.M || n >= a.N) return;
-  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(a.A) + (long long)batch * a.strideA;
-  const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(a.B) + (long long)batch * a.strideB;
+  const int bin = a.batch_inner > 1 ? a.batch_inner : 1;
+  const long long b_in = batch % bin, b_out = batch / bin;
+  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(a.A) + b_out * a.strideA + b_in * a.strideA2;
+  const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(a.B) + b_out * a.strideB + b_in * a.strideB2;
   const int ntl = (a.tap_mode == CRIS_TAP_ACCUM) ? a.taps : 1;
   float acc = 0.f;
   for (int tl = 0; tl < ntl; ++tl) {
@@ -62,12 +64,15 @@ __global__ void gemm_ref_kernel(const RefArgs r) {
   v = ref_act(v, a.act);
   const int dcol = n + ((a.tap_mode == CRIS_TAP_WGRAD) ? ztap * a.d_tap_n : 0);
   if (a.resid) {
-    const long long ri = (long long)batch * a.strideR + (long long)m * a.ldr + dcol;
+    const long long ri = b_out * a.strideR + b_in * a.strideR2 + (long long)m * a.ldr + dcol;
     v += a.resid_fp32 ? reinterpret_cast<const float*>(a.resid)[ri]
                       : bf2f(reinterpret_cast<const __nv_bfloat16*>(a.resid)[ri]);
   }
   if (!interior_row(m, a.mask_hp, a.mask_wp)) v = 0.f;
-  const long long di = (long long)batch * a.strideD + (long long)m * a.ldd + dcol;
+  long long di = b_out * a.strideD + b_in * a.strideD2 + (long long)m * a.ldd + dcol;
+  if (a.accumulate && a.d_col_stride > 1)
+    di = b_out * a.strideD + b_in * a.strideD2 + (long long)m * a.ldd + (long long)n * a.d_col_stride +
+         ((a.tap_mode == CRIS_TAP_WGRAD) ? ztap * a.d_tap_n : 0);
   if (a.d_fp32) {
     float* D = reinterpret_cast<float*>(a.D);
     if (a.accumulate) atomicAdd(D + di, v);

@@ -30,16 +30,18 @@ struct GemmKArgs {
   int tap_off[9];
   int b_tap_k, b_tap_n, d_tap_n;
   void* D;
-  long long ldd, strideD;
+  long long ldd, strideD, strideD2;
+  int batch_inner;
   int d_fp32, accumulate;
   float alpha;
   const float* bias;
   int act;
   const void* resid;
-  long long ldr, strideR;
+  long long ldr, strideR, strideR2;
   int resid_fp32;
   int mask_hp, mask_wp;
   float* colstats;
+  int d_col_stride;
 };
 
 constexpr int BM = 128;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
   z /= p.splits;
   const int ztap = z % p.taps_z;
   const int batch = z / p.taps_z;
+  const int b_in = batch % p.batch_inner, b_out = batch / p.batch_inner;
 
   // k-block schedule of this CTA
   const int kb_per_split = (p.nkb + p.splits - 1) / p.splits;
@@ -134,19 +137,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
           b_k_off = p.tap_off[t];
         }
         if constexpr (!A_MN) {
-          ptx::tma_load_3d(sa, &tmA, &full_bar[s], k, m0 + a_row_off, batch);
+          ptx::tma_load_4d(sa, &tmA, &full_bar[s], k, m0 + a_row_off, b_in, b_out);
         } else {
 #pragma unroll
           for (int i = 0; i < BM / 64; ++i)
-            ptx::tma_load_3d(sa + i * (BK * 128), &tmA, &full_bar[s], m0 + 64 * i, k, batch);
+            ptx::tma_load_4d(sa + i * (BK * 128), &tmA, &full_bar[s], m0 + 64 * i, k, b_in, b_out);
         }
         if constexpr (!B_MN) {
-          ptx::tma_load_3d(sb, &tmB, &full_bar[s], k + b_k_off, n0 + b_n_off, batch);
+          ptx::tma_load_4d(sb, &tmB, &full_bar[s], k + b_k_off, n0 + b_n_off, b_in, b_out);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
-            ptx::tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + b_n_off + 64 * j, k + b_k_off,
-                             batch);
+            ptx::tma_load_4d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + b_n_off + 64 * j, k + b_k_off,
+                             b_in, b_out);
         }
       }
     }
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     const bool row_valid = row_in && interior_row(row, p.mask_hp, p.mask_wp);
     const int dcol0 = n0 + ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
     uint8_t* Dbase = reinterpret_cast<uint8_t*>(p.D);
-    const long long drow = (long long)batch * p.strideD + row * p.ldd;
-    const long long rrow = (long long)batch * p.strideR + row * p.ldr;
+    const long long drow = (long long)b_out * p.strideD + (long long)b_in * p.strideD2 + row * p.ldd;
+    const long long rrow = (long long)b_out * p.strideR + (long long)b_in * p.strideR2 + row * p.ldr;
     if (total_iters > 0) {
       ptx::mbar_wait(tmem_full, 0, 300);
       ptx::tc_fence_after();
@@ -243,9 +246,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
         if (p.d_fp32) {
           float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
           if (p.accumulate) {
+            float* ap = reinterpret_cast<float*>(Dbase) + drow +
+                        ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) atomicAdd(dp + j, v[j]);
+              if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
           } else if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -341,22 +346,26 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // operand stored as [outer_extent][inner_extent] bf16 rows with pitch ld (elements) and batch stride
 static int make_tmap(CUtensorMap* tm, const void* base, long long inner_extent, long long outer_extent,
-                     long long ld, long long batch, long long batch_stride, int box_inner, int box_outer,
-                     CUtensorMapSwizzle swz) {
+                     long long ld, long long batch, long long batch_stride, long long batch_in,
+                     long long batch_in_stride, int box_inner, int box_outer, CUtensorMapSwizzle swz) {
   auto fn = get_encode_fn();
   CRIS_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   CRIS_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base not 16B aligned");
   CRIS_CHECK_ARG((ld * 2) % 16 == 0, "GEMM operand pitch %lld elements is not a multiple of 16 bytes", ld);
-  if (batch <= 1) {
-    batch = 1;
-    batch_stride = ld * (outer_extent > 0 ? outer_extent : 1);
+  if (batch_in <= 1) {
+    batch_in = 1;
+    batch_in_stride = ld * (outer_extent > 0 ? outer_extent : 1);
   }
-  CRIS_CHECK_ARG((batch_stride * 2) % 16 == 0, "GEMM batch stride not a multiple of 16 bytes");
-  cuuint64_t dims[3] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)(ld * 2), (cuuint64_t)(batch_stride * 2)};
-  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  const long long batch_out = batch / batch_in;
+  if (batch_out <= 1) batch_stride = batch_in_stride * batch_in;
+  CRIS_CHECK_ARG((batch_stride * 2) % 16 == 0 && (batch_in_stride * 2) % 16 == 0,
+                 "GEMM batch strides must be multiples of 16 bytes");
+  cuuint64_t dims[4] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent, (cuuint64_t)batch_in,
+                        (cuuint64_t)(batch_out > 0 ? batch_out : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * 2), (cuuint64_t)(batch_in_stride * 2), (cuuint64_t)(batch_stride * 2)};
+  cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CRIS_CHECK_ARG(r == CUDA_SUCCESS,
@@ -369,13 +378,15 @@ template <int BN, int BK, bool A_MN, bool B_MN>
 static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
   using Cfg = TileCfg<BN, BK>;
   CUtensorMap tmA, tmB;
+  const long long bin = a->batch_inner > 1 ? a->batch_inner : 1;
   const long long a_rows = a->a_rows > 0 ? a->a_rows : (A_MN ? a->K : a->M);
   const long long b_rows = a->b_rows > 0 ? a->b_rows : (B_MN ? a->K : a->N);
   int rc;
   if (A_MN)
-    rc = make_tmap(&tmA, a->A, a->M, a_rows, a->lda, a->batch, a->strideA, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tmA, a->A, a->M, a_rows, a->lda, a->batch, a->strideA, bin, a->strideA2, 64, BK,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
   else
-    rc = make_tmap(&tmA, a->A, a->K, a_rows, a->lda, a->batch, a->strideA, BK, BM,
+    rc = make_tmap(&tmA, a->A, a->K, a_rows, a->lda, a->batch, a->strideA, bin, a->strideA2, BK, BM,
                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   // B inner extent: K-major = total K over all taps; MN-major = total N over all taps
@@ -385,9 +396,10 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
   else
     b_inner = (a->tap_mode == CRIS_TAP_ACCUM && a->b_tap_k > 0) ? (long long)(a->taps - 1) * a->b_tap_k + a->K : a->K;
   if (B_MN)
-    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, bin, a->strideB2, 64, BK,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
   else
-    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, BK, BN,
+    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, bin, a->strideB2, BK, BN,
                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   GemmKArgs kk = k;
@@ -416,8 +428,10 @@ int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
   CRIS_CHECK_ARG(a->splits >= 1, "splits must be >= 1");
   CRIS_CHECK_ARG(a->splits == 1 || (a->d_fp32 && a->accumulate), "split-K needs fp32 atomic accumulation");
   CRIS_CHECK_ARG(!a->accumulate || a->d_fp32, "accumulate needs fp32 D");
+  CRIS_CHECK_ARG(a->d_col_stride <= 1 || a->accumulate, "d_col_stride needs accumulate mode");
   CRIS_CHECK_ARG(a->tap_mode != CRIS_TAP_WGRAD || (a->a_mn && a->b_mn), "wgrad tap mode needs MN-major A and B");
   CRIS_CHECK_ARG(a->tap_mode == CRIS_TAP_NONE || a->batch == 1, "tap modes are unbatched");
+  CRIS_CHECK_ARG(a->batch_inner <= 1 || a->batch % a->batch_inner == 0, "batch must be a multiple of batch_inner");
   if (g_gemm_impl.load() == 1) return gemm_ref_launch(a, stream);
 
   GemmKArgs k;
@@ -428,10 +442,14 @@ int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
   k.taps_z = a->tap_mode == CRIS_TAP_WGRAD ? a->taps : 1;
   for (int i = 0; i < 9; ++i) k.tap_off[i] = a->tap_off[i];
   k.b_tap_k = a->b_tap_k; k.b_tap_n = a->b_tap_n; k.d_tap_n = a->d_tap_n;
-  k.D = a->D; k.ldd = a->ldd; k.strideD = a->strideD; k.d_fp32 = a->d_fp32; k.accumulate = a->accumulate;
+  k.D = a->D; k.ldd = a->ldd; k.strideD = a->strideD; k.strideD2 = a->strideD2;
+  k.batch_inner = a->batch_inner > 1 ? a->batch_inner : 1;
+  k.strideR2 = a->strideR2;
+  k.d_fp32 = a->d_fp32; k.accumulate = a->accumulate;
   k.alpha = a->alpha; k.bias = a->bias; k.act = a->act;
   k.resid = a->resid; k.ldr = a->ldr; k.strideR = a->strideR; k.resid_fp32 = a->resid_fp32;
   k.mask_hp = a->mask_hp; k.mask_wp = a->mask_wp; k.colstats = a->colstats;
+  k.d_col_stride = a->d_col_stride > 0 ? a->d_col_stride : 1;
 
   const bool amn = a->a_mn != 0, bmn = a->b_mn != 0;
   const bool k32 = (a->K <= 32) && !amn && !bmn;  // stem convs: 32 input channels per tap

@@ -1,5 +1,6 @@
 // lib.cu — library-wide state of libcris_b200: error string, ABI version, device check.
 #include <stdarg.h>
+#include <stddef.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,9 @@ extern "C" {
 const char* cris_last_error(void) { return cris::g_err; }
 
 int cris_abi_version(void) { return 1; }
+
+int cris_gemm_args_size(void) { return (int)sizeof(cris_gemm_args); }
+int cris_gemm_args_last_offset(void) { return (int)offsetof(cris_gemm_args, d_col_stride); }
 
 uint64_t cris_launch_count(void) { return cris::g_launches.load(); }
 

@@ -1,0 +1,449 @@
+// norm.cu — BatchNorm (batch-statistics, two-phase) and LayerNorm kernels, forward and backward.
+// Reference call sites: nn.BatchNorm2d/1d + SyncBatchNorm (model/clip.py:18-26,171-183;
+// model/layers.py:8-16,262; train.py:97-98), nn.LayerNorm (model/clip.py:226-231,
+// model/layers.py:199-216).  All HBM-bound: 16-byte vector accesses, one pass per tensor.
+#include "vec.cuh"
+
+namespace cris {
+
+// ---------------------------------------------------------------------------------------------
+// column reductions over a [rows, C] matrix -> partials[block][2][C]
+//   MODE 0: (x, x^2)                        batch statistics of a tensor not produced by the GEMM
+//   MODE 1: (dz, dz*xhat), dz = dy*(y>0)    BatchNorm backward
+//   MODE 2: (dy, -)                         bias gradient
+//   MODE 3: (dy, dy*xhat) with per-ROW mean/rstd   LayerNorm gamma/beta gradients
+// ---------------------------------------------------------------------------------------------
+struct ColReduceArgs {
+  const void* a;  long long lda; int a_fp32;     // x (mode 0) or dy
+  const void* a2; long long lda2;                // optional second dy (bf16) added to a (mode 3)
+  const void* y;  long long ldy;                 // post-activation output (mode 1, relu mask), bf16
+  const void* x;  long long ldx; int x_fp32;     // pre-normalisation input (modes 1, 3)
+  const float* mean; const float* rstd;          // per-column (mode 1) or per-row (mode 3)
+  long long rows; int C; int relu; int hp, wp;
+  float* partials;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) {
+  __shared__ float sm[256 * 16];
+  const int G = p.C / 8;
+  const int Gp = G < 256 ? G : 256;
+  const int R = 256 / Gp;
+  const int tg = threadIdx.x % Gp, tr = threadIdx.x / Gp;
+  const long long rpb = (p.rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rpb;
+  const long long r1 = min(p.rows, r0 + rpb);
+  for (int g = tg; g < G; g += Gp) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+    const int c = g * 8;
+    float mu[8], rs[8];
+    if (MODE == 1) {
+      ld8f(p.mean + c, mu);
+      ld8f(p.rstd + c, rs);
+    }
+    if (tr < R) {
+      for (long long r = r0 + tr; r < r1; r += R) {
+        if (MODE != 3 && !interior_row(r, p.hp, p.wp)) continue;
+        float a[8];
+        ld8x(p.a, r * p.lda + c, p.a_fp32, a);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * a[i]; }
+        } else if (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s0[i] += a[i];
+        } else if (MODE == 1) {
+          float xv[8];
+          ld8x(p.x, r * p.ldx + c, p.x_fp32, xv);
+          if (p.relu) {
+            float yv[8];
+            ld8(reinterpret_cast<const __nv_bfloat16*>(p.y) + r * p.ldy + c, yv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!(yv[i] > 0.f)) a[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * (xv[i] - mu[i]) * rs[i]; }
+        } else {
+          float xv[8];
+          ld8x(p.x, r * p.ldx + c, p.x_fp32, xv);
+          if (p.a2 != nullptr) {
+            float b[8];
+            ld8(reinterpret_cast<const __nv_bfloat16*>(p.a2) + r * p.lda2 + c, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += b[i];
+          }
+          const float m = p.mean[r], s = p.rstd[r];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * (xv[i] - m) * s; }
+        }
+      }
+    }
+    // reduce over the R row-lanes that share this channel group
+    __syncthreads();
+    if (tr < R) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sm[threadIdx.x * 16 + i] = s0[i]; sm[threadIdx.x * 16 + 8 + i] = s1[i]; }
+    }
+    __syncthreads();
+    if (tr == 0) {
+      for (int rr = 1; rr < R; ++rr) {
+        const int o = (rr * Gp + tg) * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += sm[o + i]; s1[i] += sm[o + 8 + i]; }
+      }
+      float* dst = p.partials + (size_t)blockIdx.x * 2 * p.C;
+      st8f(dst + c, s0);
+      st8f(dst + p.C + c, s1);
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_tiles, int C2,
+                                       float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C2) return;
+  float s = 0.f, comp = 0.f;  // Kahan: thousands of tile partials per channel
+  for (int t = 0; t < n_tiles; ++t) {
+    const float v = partials[(size_t)t * C2 + i] - comp;
+    const float ns = s + v;
+    comp = (ns - s) - v;
+    s = ns;
+  }
+  sums[i] = s;
+}
+
+__global__ void bn_coeffs_kernel(const float* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                 float* running_var, float* scale, float* shift, float* mean_out, float* invstd_out,
+                                 int C, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = (double)sums[c] / count;
+    double v = (double)sums[C + c] / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean != nullptr) {
+      const double unb = count > 1 ? v * count / (count - 1) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float inv = rsqrtf(var + eps);
+  const float sc = gamma[c] * inv;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (invstd_out) invstd_out[c] = inv;
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ resid,
+                                long long ldr, __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int C,
+                                int relu, int hp, int wp) {
+  const int G = C / 8;
+  const long long total = rows * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float v[8];
+    if (interior_row(r, hp, wp)) {
+      float sc[8], sh[8];
+      ld8(x + r * ldx + c, v);
+      ld8f(scale + c, sc);
+      ld8f(shift + c, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+      if (resid != nullptr) {
+        float rv[8];
+        ld8(resid + r * ldr + c, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += rv[k];
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    st8(y + r * ldy + c, v);
+  }
+}
+
+// dx = gamma*invstd*(dz - s0/cnt - xhat*s1/cnt), dz = dy*(y>0); optional dres (+)= dz
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                    const __nv_bfloat16* __restrict__ y, long long ldy,
+                                    const __nv_bfloat16* __restrict__ x, long long ldx,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
+                                    __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
+                                    long long lddres, int dres_accumulate, long long rows, int C, int relu, int hp,
+                                    int wp) {
+  const int G = C / 8;
+  const long long total = rows * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float o[8], dz[8];
+    if (interior_row(r, hp, wp)) {
+      float xv[8], mu[8], is[8], ga[8], s0[8], s1[8];
+      ld8(dy + r * lddy + c, dz);
+      if (relu) {
+        float yv[8];
+        ld8(y + r * ldy + c, yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) dz[k] = 0.f;
+      }
+      ld8(x + r * ldx + c, xv);
+      ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga);
+      ld8f(sums + c, s0); ld8f(sums + C + c, s1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - mu[k]) * is[k];
+        o[k] = ga[k] * is[k] * (dz[k] - s0[k] * inv_count - xh * s1[k] * inv_count);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = dz[k] = 0.f;
+    }
+    st8(dx + r * lddx + c, o);
+    if (dres != nullptr) {
+      if (dres_accumulate) {
+        float old[8];
+        ld8(dres + r * lddres + c, old);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dz[k] += old[k];
+      }
+      st8(dres + r * lddres + c, dz);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, C % 128 == 0, C <= 2048.  y = xhat*gamma+beta (bf16 or fp32),
+// optional y2 = y + add[row % add_period] (bf16) — the "+ positional encoding" copy fed to q/k.
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+    layernorm_fwd_kernel(const void* __restrict__ x, int x_fp32, long long ldx, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ add, long long ldadd,
+                         int add_period, void* __restrict__ y, int y_fp32, long long ldy,
+                         __nv_bfloat16* __restrict__ y2, long long ldy2, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = C / 128;
+  float v[MAXV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      ld4x(x, row * ldx + i * 128 + lane * 4, x_fp32, v[i]);
+      s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float d = v[i][k] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      float o[4];
+      o[0] = (v[i][0] - mean) * rstd * g.x + b.x;
+      o[1] = (v[i][1] - mean) * rstd * g.y + b.y;
+      o[2] = (v[i][2] - mean) * rstd * g.z + b.z;
+      o[3] = (v[i][3] - mean) * rstd * g.w + b.w;
+      if (y != nullptr) st4x(y, row * ldy + c, y_fp32, o);
+      if (y2 != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(add + (row % add_period) * ldadd + c);
+        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+        st4x(y2, row * ldy2 + c, 0, o);
+      }
+    }
+  }
+}
+
+// dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = (dy + dy2)*gamma
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, long long lddy,
+                         const __nv_bfloat16* __restrict__ dy2, long long lddy2, const void* __restrict__ x,
+                         int x_fp32, long long ldx, const float* __restrict__ gamma, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, void* __restrict__ dx, int dx_fp32, long long lddx,
+                         int dx_accumulate, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = C / 128;
+  const float mu = mean[row], rs = rstd[row];
+  float g[MAXV][4], xh[MAXV][4];
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      float d[4], xv[4];
+      ld4x(dy, row * lddy + c, dy_fp32, d);
+      if (dy2 != nullptr) {
+        float d2[4];
+        ld4x(dy2, row * lddy2 + c, 0, d2);
+        d[0] += d2[0]; d[1] += d2[1]; d[2] += d2[2]; d[3] += d2[3];
+      }
+      ld4x(x, row * ldx + c, x_fp32, xv);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+      const float gg[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xh[i][k] = (xv[k] - mu) * rs;
+        g[i][k] = d[k] * gg[k];
+        sg += g[i][k];
+        sgx += g[i][k] * xh[i][k];
+      }
+    }
+  }
+  const float mg = warp_sum(sg) / C, mgx = warp_sum(sgx) / C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = rs * (g[i][k] - mg - xh[i][k] * mgx);
+      if (dx_accumulate) {
+        float old[4];
+        ld4x(dx, row * lddx + c, dx_fp32, old);
+        o[0] += old[0]; o[1] += old[1]; o[2] += old[2]; o[3] += old[3];
+      }
+      st4x(dx, row * lddx + c, dx_fp32, o);
+    }
+  }
+}
+
+}  // namespace cris
+
+using namespace cris;
+
+extern "C" {
+
+int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void* a2, int64_t lda2, const void* y,
+                    int64_t ldy, const void* x, int64_t ldx, int x_fp32, const float* mean, const float* rstd,
+                    int64_t rows, int C, int relu, int hp, int wp, float* partials, int n_blocks, void* stream) {
+  CRIS_CHECK_ARG(C % 8 == 0 && C <= 2048, "col_reduce: C=%d must be a multiple of 8 and <= 2048", C);
+  CRIS_CHECK_ARG(n_blocks >= 1, "col_reduce: n_blocks");
+  ColReduceArgs p{a, lda, a_fp32, a2, lda2, y, ldy, x, ldx, x_fp32, mean, rstd, rows, C, relu, hp, wp, partials};
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (mode) {
+    case 0: col_reduce_kernel<0><<<n_blocks, 256, 0, s>>>(p); break;
+    case 1: col_reduce_kernel<1><<<n_blocks, 256, 0, s>>>(p); break;
+    case 2: col_reduce_kernel<2><<<n_blocks, 256, 0, s>>>(p); break;
+    case 3: col_reduce_kernel<3><<<n_blocks, 256, 0, s>>>(p); break;
+    default: set_error("col_reduce: bad mode %d", mode); return -1;
+  }
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums, void* stream) {
+  reduce_partials_kernel<<<(2 * C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles,
+                                                                                                 2 * C, sums);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_bn_coeffs(const float* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                   float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                   int C, int training, void* stream) {
+  bn_coeffs_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd, C, training);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift, const void* resid, int64_t ldr,
+                  void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream) {
+  CRIS_CHECK_ARG(C % 8 == 0, "bn_apply: C=%d must be a multiple of 8", C);
+  const long long work = rows * (C / 8);
+  bn_apply_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, scale, shift, reinterpret_cast<const __nv_bfloat16*>(resid), ldr,
+      reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, relu, hp, wp);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
+                      const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
+                      void* dx, int64_t lddx, void* dres, int64_t lddres, int dres_accumulate, int64_t rows, int C,
+                      int relu, int hp, int wp, void* stream) {
+  CRIS_CHECK_ARG(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long work = rows * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), ldy,
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean, invstd, gamma, sums, (float)(1.0 / count),
+      reinterpret_cast<__nv_bfloat16*>(dx), lddx, reinterpret_cast<__nv_bfloat16*>(dres), lddres, dres_accumulate,
+      rows, C, relu, hp, wp);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_layernorm_fwd(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, const float* add,
+                       int64_t ldadd, int add_period, void* y, int y_fp32, int64_t ldy, void* y2, int64_t ldy2,
+                       float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+  CRIS_CHECK_ARG(C % 128 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 128 and <= 2048", C);
+  const int grid = (int)((rows + 7) / 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (C <= 512)
+    layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, x_fp32, ldx, gamma, beta, add, ldadd, add_period > 0 ? add_period : 1,
+                                                 y, y_fp32, ldy, reinterpret_cast<__nv_bfloat16*>(y2), ldy2, mean, rstd,
+                                                 rows, C, eps);
+  else
+    layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_fp32, ldx, gamma, beta, add, ldadd,
+                                                  add_period > 0 ? add_period : 1, y, y_fp32, ldy,
+                                                  reinterpret_cast<__nv_bfloat16*>(y2), ldy2, mean, rstd, rows, C, eps);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+
+int cris_layernorm_bwd(const void* dy, int dy_fp32, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
+                       int x_fp32, int64_t ldx, const float* gamma, const float* mean, const float* rstd, void* dx,
+                       int dx_fp32, int64_t lddx, int dx_accumulate, int64_t rows, int C, void* stream) {
+  CRIS_CHECK_ARG(C % 128 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 128 and <= 2048", C);
+  const int grid = (int)((rows + 7) / 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (C <= 512)
+    layernorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2,
+                                                 x, x_fp32, ldx, gamma, mean, rstd, dx, dx_fp32, lddx, dx_accumulate,
+                                                 rows, C);
+  else
+    layernorm_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2,
+                                                  x, x_fp32, ldx, gamma, mean, rstd, dx, dx_fp32, lddx, dx_accumulate,
+                                                  rows, C);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+}

@@ -1,0 +1,377 @@
+// tokens.cu — row softmax (attention probabilities) fwd/bwd, token embedding, EOT gather, residual
+// add + dropout, QuickGELU, casts / packing, small reductions.
+// Reference call sites: softmax/dropout inside F.multi_head_attention_forward (model/clip.py:119-139,
+// 255-260; model/layers.py:235,240-243), nn.Embedding + positional add (clip.py:440-443), EOT gather
+// (clip.py:451-452), nn.Dropout + residual adds (layers.py:237,245,249), QuickGELU (clip.py:234-236).
+#include "vec.cuh"
+
+namespace cris {
+
+// ---- softmax over rows of S[nb][Lq][ld] (scores already scaled by the GEMM alpha) ----------------
+// One warp per row; Lk <= 32*MAXE.  causal: key j > query i masked.  key padding: kpm[b][j] != 0 masked,
+// b = batch_index / heads.  P (bf16) = softmax; Pd (optional) = dropout(P) * 1/(1-p).
+template <int MAXE>
+__global__ void __launch_bounds__(256)
+    softmax_fwd_kernel(const __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ P,
+                       __nv_bfloat16* __restrict__ Pd, long long ld, long long batch_stride, int nb, int Lq, int Lk,
+                       int heads, const uint8_t* __restrict__ kpm, int causal, float p_drop, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const long long rid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (rid >= (long long)nb * Lq) return;
+  const int bi = (int)(rid / Lq), qi = (int)(rid % Lq);
+  const long long off = (long long)bi * batch_stride + (long long)qi * ld;
+  const uint8_t* km = kpm ? kpm + (long long)(bi / heads) * Lk : nullptr;
+  float v[MAXE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = e * 32 + lane;
+    float x = -INFINITY;
+    if (j < Lk) {
+      x = bf2f(S[off + j]);
+      if ((causal && j > qi) || (km && km[j])) x = -INFINITY;
+    }
+    v[e] = x;
+    mx = fmaxf(mx, x);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    v[e] = (v[e] == -INFINITY) ? 0.f : __expf(v[e] - mx);
+    sum += v[e];
+  }
+  sum = warp_sum(sum);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  const uint32_t th = drop_thresh(p_drop);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = e * 32 + lane;
+    if (j < Lk) {
+      const float pr = v[e] * inv;
+      P[off + j] = f2bf(pr);
+      if (Pd != nullptr) Pd[off + j] = f2bf(drop_keep(seed, (uint64_t)(off + j), th) ? pr * keep_scale : 0.f);
+    }
+  }
+}
+
+// dS = P * (dPm - sum_j P*dPm), dPm = dP * dropmask/(1-p);  written in place of dP (bf16)
+template <int MAXE>
+__global__ void __launch_bounds__(256)
+    softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dP, long long ld,
+                       long long batch_stride, int nb, int Lq, int Lk, float p_drop, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const long long rid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (rid >= (long long)nb * Lq) return;
+  const int bi = (int)(rid / Lq), qi = (int)(rid % Lq);
+  const long long off = (long long)bi * batch_stride + (long long)qi * ld;
+  const uint32_t th = drop_thresh(p_drop);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float pv[MAXE], dv[MAXE];
+  float dot = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = e * 32 + lane;
+    pv[e] = dv[e] = 0.f;
+    if (j < Lk) {
+      pv[e] = bf2f(P[off + j]);
+      float d = bf2f(dP[off + j]);
+      if (p_drop > 0.f) d = drop_keep(seed, (uint64_t)(off + j), th) ? d * keep_scale : 0.f;
+      dv[e] = d;
+      dot += pv[e] * d;
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = e * 32 + lane;
+    if (j < Lk) dP[off + j] = f2bf(pv[e] * (dv[e] - dot));
+  }
+}
+
+// ---- token embedding + positional embedding -> fp32 residual stream ----------------------------
+__global__ void embed_fwd_kernel(const long long* __restrict__ word, const float* __restrict__ table,
+                                 const float* __restrict__ pos, float* __restrict__ x, int B, int L, int C) {
+  const int G = C / 4;
+  const long long total = (long long)B * L * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long t = i / G;
+    const int l = (int)(t % L);
+    const long long tokid = word[t];
+    const float4 a = *reinterpret_cast<const float4*>(table + tokid * C + g * 4);
+    const float4 b = *reinterpret_cast<const float4*>(pos + (long long)l * C + g * 4);
+    *reinterpret_cast<float4*>(x + t * C + g * 4) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+// dtable[word] += dx (atomic), dpos[l] += sum_b dx
+__global__ void embed_bwd_kernel(const long long* __restrict__ word, const float* __restrict__ dx,
+                                 float* __restrict__ dtable, float* __restrict__ dpos, int B, int L, int C) {
+  const long long total = (long long)B * L * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int l = (int)(t % L);
+    const float g = dx[i];
+    atomicAdd(dtable + word[t] * C + c, g);
+    atomicAdd(dpos + (long long)l * C + c, g);
+  }
+}
+
+// ---- EOT gather: out[b, :] = x[b*L + argmax_l word[b, l], :] (first maximum, like torch.argmax) ----
+__global__ void eot_gather_kernel(const long long* __restrict__ word, const void* __restrict__ x, int x_fp32,
+                                  long long ldx, __nv_bfloat16* __restrict__ out, long long ldo, int L, int C) {
+  const int b = blockIdx.x;
+  int best = 0;
+  long long bv = word[(long long)b * L];
+  for (int l = 1; l < L; ++l) {
+    const long long v = word[(long long)b * L + l];
+    if (v > bv) { bv = v; best = l; }
+  }
+  const long long row = (long long)b * L + best;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = x_fp32 ? reinterpret_cast<const float*>(x)[row * ldx + c]
+                           : bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[row * ldx + c]);
+    out[(long long)b * ldo + c] = f2bf(v);
+  }
+}
+// dx[b*L + eot, :] += dout[b, :]
+__global__ void eot_scatter_kernel(const long long* __restrict__ word, const void* __restrict__ dout, int d_fp32,
+                                   long long ldd, void* __restrict__ dx, int dx_fp32, long long lddx, int L, int C) {
+  const int b = blockIdx.x;
+  int best = 0;
+  long long bv = word[(long long)b * L];
+  for (int l = 1; l < L; ++l) {
+    const long long v = word[(long long)b * L + l];
+    if (v > bv) { bv = v; best = l; }
+  }
+  const long long row = (long long)b * L + best;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = d_fp32 ? reinterpret_cast<const float*>(dout)[(long long)b * ldd + c]
+                           : bf2f(reinterpret_cast<const __nv_bfloat16*>(dout)[(long long)b * ldd + c]);
+    if (dx_fp32) reinterpret_cast<float*>(dx)[row * lddx + c] += g;
+    else {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx) + row * lddx + c;
+      *p = f2bf(bf2f(*p) + g);
+    }
+  }
+}
+
+// ---- generic elementwise over a [rows, C] matrix (C % 4 == 0) ---------------------------------------
+//   OP 0: out = a (+ b)                                     (cast / add; any dtype mix)
+//   OP 1: out = a + dropout(b)                              residual add with dropout (mask from seed)
+//   OP 2: out = dropout(a)                                  (backward of OP 1 w.r.t. b; also plain dropout)
+//   OP 3: out = quickgelu(a)
+//   OP 4: out = b * quickgelu'(a)                           (a = pre-activation, b = upstream grad)
+//   OP 5: out = (a > 0) ? b : 0                             relu backward (a = activation output)
+struct EwArgs {
+  const void* a; int a_fp32; long long lda;
+  const void* b; int b_fp32; long long ldb;
+  void* out; int out_fp32; long long ldo;
+  long long rows; int C;
+  float p_drop; uint64_t seed;
+};
+template <int OP>
+__global__ void ew_kernel(const EwArgs p) {
+  const int G = p.C / 4;
+  const long long total = p.rows * G;
+  const uint32_t th = drop_thresh(p.p_drop);
+  const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / G;
+    const int c = (int)(i - r * G) * 4;
+    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, o[4];
+    if (p.a != nullptr) ld4x(p.a, r * p.lda + c, p.a_fp32, a);
+    if (p.b != nullptr) ld4x(p.b, r * p.ldb + c, p.b_fp32, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t idx = (uint64_t)(r * p.C + c + k);
+      if (OP == 0) o[k] = a[k] + b[k];
+      else if (OP == 1) o[k] = a[k] + ((p.p_drop > 0.f) ? (drop_keep(p.seed, idx, th) ? b[k] * ks : 0.f) : b[k]);
+      else if (OP == 2) o[k] = (p.p_drop > 0.f) ? (drop_keep(p.seed, idx, th) ? a[k] * ks : 0.f) : a[k];
+      else if (OP == 3) o[k] = a[k] / (1.f + __expf(-1.702f * a[k]));
+      else if (OP == 4) {
+        const float s = 1.f / (1.f + __expf(-1.702f * a[k]));
+        o[k] = b[k] * (s + 1.702f * a[k] * s * (1.f - s));
+      } else o[k] = a[k] > 0.f ? b[k] : 0.f;
+    }
+    st4x(p.out, r * p.ldo + c, p.out_fp32, o);
+  }
+}
+
+// ---- weight packing: fp32 OIHW [Cout][Cin][taps] -> bf16 [Cout][taps][cin_pad] (zero padded) ----------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                        int Cin, int taps, int cin_pad) {
+  const long long total = (long long)Cout * taps * cin_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int t = (int)((i / cin_pad) % taps);
+    const int co = (int)(i / ((long long)cin_pad * taps));
+    out[i] = f2bf(ci < Cin ? w[((long long)co * Cin + ci) * taps + t] : 0.f);
+  }
+}
+// fp32 [rows][cols] -> bf16 [rows][ld] (zero padded), optional per-row scale
+__global__ void pack_matrix_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long rows,
+                                   int cols, int ld) {
+  const long long total = rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    const long long r = i / ld;
+    out[i] = f2bf(c < cols ? w[r * cols + c] : 0.f);
+  }
+}
+// out[t, c] (+)= sum_b in[b*T + t, c]   (batch reduction of token gradients -> shared positional term)
+__global__ void batch_reduce_kernel(const void* __restrict__ in, int in_fp32, long long ldin, float* __restrict__ out,
+                                    long long ldo, int B, int T, int C, int accumulate) {
+  const long long total = (long long)T * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int t = (int)(i / C);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long idx = ((long long)b * T + t) * ldin + c;
+      s += in_fp32 ? reinterpret_cast<const float*>(in)[idx] : bf2f(reinterpret_cast<const __nv_bfloat16*>(in)[idx]);
+    }
+    if (accumulate) out[(long long)t * ldo + c] += s;
+    else out[(long long)t * ldo + c] = s;
+  }
+}
+// small dense fp32 matmul (batch-independent glue only: bicubic positional-embedding resize,
+// 169x49 by 49xC): out[m, c] = sum_k R[m, k] * X[k, c]   or with transpose_r: out[k, c] = sum_m R[m,k] * X[m,c]
+__global__ void small_matmul_kernel(const float* __restrict__ R, const float* __restrict__ X, float* __restrict__ out,
+                                    int M, int K, int C, int transpose_r, int accumulate) {
+  const int rows_out = transpose_r ? K : M;
+  const int red = transpose_r ? M : K;
+  const long long total = (long long)rows_out * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int ro = (int)(i / C);
+    float s = 0.f;
+    for (int j = 0; j < red; ++j) {
+      const float rv = transpose_r ? R[(long long)j * K + ro] : R[(long long)ro * K + j];
+      s = fmaf(rv, X[(long long)j * C + c], s);
+    }
+    if (accumulate) out[i] += s;
+    else out[i] = s;
+  }
+}
+
+}  // namespace cris
+
+using namespace cris;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
+                     int heads, const uint8_t* kpm, int causal, float p_drop, uint64_t seed, void* stream) {
+  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 32 * 22, "softmax: Lk=%d out of range (max 704)", Lk);
+  const int grid = (int)(((long long)nb * Lq + 7) / 8);
+  if (Lk <= 32)
+    softmax_fwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
+                                                     causal, p_drop, seed);
+  else if (Lk <= 192)
+    softmax_fwd_kernel<6><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
+                                                     causal, p_drop, seed);
+  else
+    softmax_fwd_kernel<22><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
+                                                      causal, p_drop, seed);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
+                     uint64_t seed, void* stream) {
+  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 32 * 22, "softmax: Lk=%d out of range (max 704)", Lk);
+  const int grid = (int)(((long long)nb * Lq + 7) / 8);
+  if (Lk <= 32)
+    softmax_bwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+  else if (Lk <= 192)
+    softmax_bwd_kernel<6><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+  else
+    softmax_bwd_kernel<22><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_embed_fwd(const int64_t* word, const float* table, const float* pos, float* x, int B, int L, int C,
+                   void* stream) {
+  CRIS_CHECK_ARG(C % 4 == 0, "embed: C=%d", C);
+  embed_fwd_kernel<<<grid_for((long long)B * L * (C / 4), 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const long long*>(word), table, pos, x, B, L, C);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_embed_bwd(const int64_t* word, const float* dx, float* dtable, float* dpos, int B, int L, int C,
+                   void* stream) {
+  embed_bwd_kernel<<<grid_for((long long)B * L * C, 256), 256, 0, STREAM>>>(reinterpret_cast<const long long*>(word),
+                                                                           dx, dtable, dpos, B, L, C);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_eot_gather(const int64_t* word, const void* x, int x_fp32, int64_t ldx, void* out, int64_t ldo, int B, int L,
+                    int C, void* stream) {
+  eot_gather_kernel<<<B, 128, 0, STREAM>>>(reinterpret_cast<const long long*>(word), x, x_fp32, ldx, BF(out), ldo, L,
+                                           C);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_eot_scatter(const int64_t* word, const void* dout, int d_fp32, int64_t ldd, void* dx, int dx_fp32,
+                     int64_t lddx, int B, int L, int C, void* stream) {
+  eot_scatter_kernel<<<B, 128, 0, STREAM>>>(reinterpret_cast<const long long*>(word), dout, d_fp32, ldd, dx, dx_fp32,
+                                            lddx, L, C);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void* b, int b_fp32, int64_t ldb, void* out,
+                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, void* stream) {
+  CRIS_CHECK_ARG(C % 4 == 0, "elementwise: C=%d must be a multiple of 4", C);
+  EwArgs p{a, a_fp32, lda, b, b_fp32, ldb, out, out_fp32, ldo, rows, C, p_drop, seed};
+  const int grid = grid_for(rows * (C / 4), 256);
+  switch (op) {
+    case 0: ew_kernel<0><<<grid, 256, 0, STREAM>>>(p); break;
+    case 1: ew_kernel<1><<<grid, 256, 0, STREAM>>>(p); break;
+    case 2: ew_kernel<2><<<grid, 256, 0, STREAM>>>(p); break;
+    case 3: ew_kernel<3><<<grid, 256, 0, STREAM>>>(p); break;
+    case 4: ew_kernel<4><<<grid, 256, 0, STREAM>>>(p); break;
+    case 5: ew_kernel<5><<<grid, 256, 0, STREAM>>>(p); break;
+    default: set_error("elementwise: bad op %d", op); return -1;
+  }
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream) {
+  pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
+                                                                                             taps, cin_pad);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream) {
+  pack_matrix_kernel<<<grid_for(rows * ld, 256), 256, 0, STREAM>>>(w, BF(out), rows, cols, ld);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_batch_reduce(const void* in, int in_fp32, int64_t ldin, float* out, int64_t ldo, int B, int T, int C,
+                      int accumulate, void* stream) {
+  batch_reduce_kernel<<<grid_for((long long)T * C, 256), 256, 0, STREAM>>>(in, in_fp32, ldin, out, ldo, B, T, C,
+                                                                          accumulate);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_small_matmul(const float* R, const float* X, float* out, int M, int K, int C, int transpose_r, int accumulate,
+                      void* stream) {
+  const int rows_out = transpose_r ? K : M;
+  small_matmul_kernel<<<grid_for((long long)rows_out * C, 256), 256, 0, STREAM>>>(R, X, out, M, K, C, transpose_r,
+                                                                                 accumulate);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+}

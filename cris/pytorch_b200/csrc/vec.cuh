@@ -1,0 +1,77 @@
+// vec.cuh — 8-wide bf16 / fp32 vector access helpers for the HBM-bound elementwise kernels.
+#pragma once
+#include "common.cuh"
+
+namespace cris {
+
+// 8 consecutive bf16 (16-byte aligned) <-> 8 floats
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* v) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void ld8f(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8f(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// dtype-flagged access: fp32 != 0 -> float storage, else bf16
+__device__ __forceinline__ void ld8x(const void* base, long long idx, int fp32, float* v) {
+  if (fp32) ld8f(reinterpret_cast<const float*>(base) + idx, v);
+  else ld8(reinterpret_cast<const __nv_bfloat16*>(base) + idx, v);
+}
+__device__ __forceinline__ void st8x(void* base, long long idx, int fp32, const float* v) {
+  if (fp32) st8f(reinterpret_cast<float*>(base) + idx, v);
+  else st8(reinterpret_cast<__nv_bfloat16*>(base) + idx, v);
+}
+__device__ __forceinline__ void ld4x(const void* base, long long idx, int fp32, float* v) {
+  if (fp32) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+    const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+}
+__device__ __forceinline__ void st4x(void* base, long long idx, int fp32, const float* v) {
+  if (fp32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint2 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = q;
+  }
+}
+
+// counter-based dropout RNG: keep iff hash(seed, index) >= p * 2^32.  The mask is a pure function of
+// (seed, element index) so backward regenerates it instead of storing it.
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+  return mix32(seed * 0x9E3779B97F4A7C15ULL + idx) >= thresh;
+}
+__host__ __device__ inline uint32_t drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+}
+
+inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace cris

@@ -85,48 +85,113 @@ typedef struct cris_gemm_args {
   int32_t mask_hp, mask_wp;
   float*  colstats;          /* [ceil(M/128)][2][N] fp32 or NULL */
   int32_t a_rows, b_rows;    /* physical row extents of A/B for OOB zero fill (0 = derive) */
+  /* two-level batch: batch index z -> (outer = z / batch_inner, inner = z % batch_inner); the outer level
+   * uses strideA/B/D/R above, the inner level the strides below (attention heads: inner = head, stride 64) */
+  int32_t batch_inner;       /* 0/1 = single-level batch */
+  int64_t strideA2, strideB2, strideD2, strideR2;
+  int32_t d_col_stride;      /* accumulate mode only: element stride between D columns (0/1 = dense);
+                                lets a 3x3 wgrad land directly in the OIHW fp32 gradient */
 } cris_gemm_args;
 
 int cris_gemm(const cris_gemm_args* args, void* stream);
+int cris_gemm_args_size(void);         /* sizeof(cris_gemm_args): lets a binding verify its struct mirror */
+int cris_gemm_args_last_offset(void);  /* offsetof(cris_gemm_args, d_col_stride) */
 
-/* ---- normalisation -------------------------------------------------------------------- */
+/* ---- column reductions / BatchNorm ------------------------------------------------------ */
 /*
- * BatchNorm (training: batch statistics; replaces nn.BatchNorm2d/1d + SyncBatchNorm,
- * model/clip.py:18-26,171-183, model/layers.py:8-16,262; torch/nn/modules/_functions.py).
- * cris_bn_finalize reduces colstats partials -> local (sum, sumsq) in stats[2][C];
- * after the optional cross-rank exchange the caller passes the global sums here again via
- * cris_bn_coeffs to get scale/shift and update running stats (momentum, unbiased var).
+ * Column reduction of a [rows, C] matrix into partials[n_blocks][2][C] (fp32):
+ *   mode 0: (sum x, sum x^2)                       batch statistics (nn.BatchNorm2d training,
+ *                                                  model/clip.py:18-26,171-183; model/layers.py:8-16,262)
+ *   mode 1: (sum dz, sum dz*xhat), dz = dy*(y>0)   BatchNorm backward (batch_norm_backward_reduce)
+ *   mode 2: (sum dy, -)                            bias gradients of nn.Linear / Conv2d(bias=True)
+ *   mode 3: (sum dy, sum dy*xhat), per-ROW mean/rstd   LayerNorm gamma/beta gradients
+ * hp/wp > 0 skips the zero border rows of a padded-NHWC matrix.
  */
-int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums /*[2][C]*/,
-                            void* stream);
-int cris_bn_coeffs(const float* sums /*[2][C]*/, double count, const float* gamma, const float* beta,
-                   float eps, float momentum, float* running_mean, float* running_var,
-                   float* scale, float* shift, float* mean, float* invstd, int C, int training,
-                   void* stream);
-/* y = mask(act(x*scale[c] + shift[c] (+ resid)))   over a padded-NHWC row matrix [rows, C] */
-int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift,
-                  const void* resid, int64_t ldr, void* y, int64_t ldy, int64_t rows, int C,
-                  int relu, int hp, int wp, void* stream);
-/* backward: dz = dy * (y > 0) if relu; sums[0][c] = sum dz, sums[1][c] = sum dz * xhat */
-int cris_bn_bwd_reduce(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x,
-                       int64_t ldx, const float* mean, const float* invstd, int64_t rows, int C,
-                       int relu, float* partials /*[n_blocks][2][C]*/, int n_blocks, void* stream);
-/* dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count); dres = dz (optional) */
-int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x,
-                      int64_t ldx, const float* mean, const float* invstd, const float* gamma,
-                      const float* sums, double count, void* dx, int64_t lddx, void* dres,
-                      int64_t lddres, int64_t rows, int C, int relu, int hp, int wp, void* stream);
+int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void* a2, int64_t lda2, const void* y,
+                    int64_t ldy, const void* x, int64_t ldx, int x_fp32, const float* mean, const float* rstd,
+                    int64_t rows, int C, int relu, int hp, int wp, float* partials, int n_blocks, void* stream);
+/* sums[2][C] = sum over tiles of partials[n_tiles][2][C] (GEMM-epilogue or col_reduce partials) */
+int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums, void* stream);
+/*
+ * (sum, sumsq, count) -> scale/shift (+ mean, invstd) and the running-stat update (momentum, unbiased
+ * variance) — torch batch_norm_gather_stats_with_counts semantics; under SyncBN the caller all-reduces
+ * `sums` across ranks first and passes the global count.  training = 0 uses the running statistics.
+ */
+int cris_bn_coeffs(const float* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                   float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                   int C, int training, void* stream);
+/* y = mask(relu?(x*scale[c] + shift[c] (+ resid))) over a padded-NHWC row matrix [rows, C] (bf16) */
+int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift, const void* resid, int64_t ldr,
+                  void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream);
+/* dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count); optional dres (+)= dz (residual branch) */
+int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
+                      const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
+                      void* dx, int64_t lddx, void* dres, int64_t lddres, int dres_accumulate, int64_t rows, int C,
+                      int relu, int hp, int wp, void* stream);
 
-/* LayerNorm over the last dim (nn.LayerNorm, model/clip.py:226-231; model/layers.py:199-216) */
-int cris_layernorm_fwd(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta,
-                       const void* add, int64_t ldadd, int add_period, void* y, int y_fp32, int64_t ldy,
-                       void* y2, int64_t ldy2, float* mean, float* rstd, int64_t rows, int C, float eps,
-                       void* stream);
-int cris_layernorm_bwd(const void* dy, int dy_fp32, int64_t lddy, const void* dy2, int64_t lddy2,
-                       const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* mean,
-                       const float* rstd, void* dx, int dx_fp32, int64_t lddx, int dx_accumulate,
-                       float* dgamma_partials, float* dbeta_partials, int n_blocks, int64_t rows, int C,
-                       void* stream);
+/* ---- LayerNorm (nn.LayerNorm; model/clip.py:226-231, model/layers.py:199-216) --------------- */
+/* y = LN(x); optional y2 = y + add[row % add_period] (bf16) — the "+ positional encoding" copy for q/k */
+int cris_layernorm_fwd(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, const float* add,
+                       int64_t ldadd, int add_period, void* y, int y_fp32, int64_t ldy, void* y2, int64_t ldy2,
+                       float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+int cris_layernorm_bwd(const void* dy, int dy_fp32, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
+                       int x_fp32, int64_t ldx, const float* gamma, const float* mean, const float* rstd, void* dx,
+                       int dx_fp32, int64_t lddx, int dx_accumulate, int64_t rows, int C, void* stream);
+
+/* ---- spatial ops on padded NHWC (nn.AvgPool2d clip.py:23,35,184; F.interpolate bilinear layers.py:54-56,293,304;
+ *      f5*state layers.py:290; reshape/permute glue clip.py:113-118,140, layers.py:166,179; CoordConv
+ *      layers.py:30-39; stem conv1 clip.py:165-170) ------------------------------------------------ */
+int cris_avgpool2_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int N, int H, int W, int C, void* stream);
+int cris_avgpool2_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int accumulate, int N, int H, int W, int C,
+                      void* stream);
+int cris_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int N, int H, int W, int C, void* stream);
+int cris_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int accumulate, int N, int H, int W,
+                        int C, void* stream);
+int cris_mul_bcast(const void* x, int64_t ldx, const void* s, int64_t lds, void* y, int64_t ldy, int64_t rows,
+                   int rows_per_image, int C, void* stream);
+int cris_mul_bcast_bwd_s(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* ds, int n_images,
+                         int rows_per_image, int C, void* stream);
+int cris_padded_to_tokens(const void* x, int64_t ldx, const float* add, int64_t ldadd, void* tok, int tok_fp32,
+                          int64_t ldt, int N, int H, int W, int C, void* stream);
+int cris_tokens_to_padded(const void* tok, int tok_fp32, int64_t ldt, void* y, int64_t ldy, int N, int H, int W, int C,
+                          void* stream);
+int cris_coord_fill(void* buf, int64_t ld, int c0, int N, int H, int W, void* stream);
+int cris_stem_conv1_fwd(const float* img, const float* w, void* z, int64_t ldz, int N, int Hin, int Win, int Cout,
+                        void* stream);
+int cris_stem_conv1_wgrad(const float* img, const void* dz, int64_t lddz, float* dw, int N, int Hin, int Win, int Cout,
+                          void* stream);
+
+/* ---- token ops (softmax/dropout inside MHA clip.py:119-139,255-260, layers.py:235,240-243; nn.Embedding
+ *      clip.py:440-443; EOT gather clip.py:451-452; residual dropout layers.py:237,245,249; QuickGELU clip.py:234-236) */
+int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
+                     int heads, const uint8_t* kpm, int causal, float p_drop, uint64_t seed, void* stream);
+int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
+                     uint64_t seed, void* stream);
+int cris_embed_fwd(const int64_t* word, const float* table, const float* pos, float* x, int B, int L, int C,
+                   void* stream);
+int cris_embed_bwd(const int64_t* word, const float* dx, float* dtable, float* dpos, int B, int L, int C,
+                   void* stream);
+int cris_eot_gather(const int64_t* word, const void* x, int x_fp32, int64_t ldx, void* out, int64_t ldo, int B, int L,
+                    int C, void* stream);
+int cris_eot_scatter(const int64_t* word, const void* dout, int d_fp32, int64_t ldd, void* dx, int dx_fp32,
+                     int64_t lddx, int B, int L, int C, void* stream);
+/* op 0: a(+b)  1: a+dropout(b)  2: dropout(a)  3: quickgelu(a)  4: b*quickgelu'(a)  5: (a>0)?b:0 */
+int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void* b, int b_fp32, int64_t ldb, void* out,
+                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, void* stream);
+int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream);
+int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
+int cris_batch_reduce(const void* in, int in_fp32, int64_t ldin, float* out, int64_t ldo, int B, int T, int C,
+                      int accumulate, void* stream);
+int cris_small_matmul(const float* R, const float* X, float* out, int M, int K, int C, int transpose_r, int accumulate,
+                      void* stream);
+
+/* ---- text-to-pixel head + loss (Projector grouped conv model/layers.py:71-84; nearest mask resize + BCE
+ *      model/segmenter.py:56-59) ------------------------------------------------------------------------ */
+int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt, const float* mask, int Hm, int Wm,
+                         float* pred, float* mask_out, float* loss_sum, int B, int H, int W, int C, void* stream);
+int cris_dynconv_bce_bwd(const void* x, int64_t ldx, const float* t, int64_t ldt, const float* pred,
+                         const float* target, const float* g, float* dl, void* dx, int64_t lddx, float* dt,
+                         int64_t lddt, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -200,3 +200,24 @@ def make_inputs(batch: int, seed: int = 0, size: int = 416, word_len: int = 17, 
         d = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2
         mask[b, 0] = torch.clamp((1.15 - d) * 4.0, 0, 1)
     return img, word, mask
+
+
+def save_clip_torchscript(sd: Dict[str, torch.Tensor], path: str, drop_connect: bool = True) -> None:
+    """Write a TorchScript file whose `.state_dict()` equals `sd` — a stand-in for OpenAI's RN50.pt that
+    `torch.jit.load(cfg.clip_pretrain).state_dict()` (model/segmenter.py:14-15) can consume.  OpenAI files do
+    not carry the CRIS-added `visual.attnpool.connect.*`, so those keys are dropped by default."""
+    root = torch.nn.Module()
+    for k, v in sd.items():
+        if drop_connect and ".connect." in k:
+            continue
+        parts = k.split(".")
+        m = root
+        for p in parts[:-1]:
+            if not hasattr(m, p):
+                m.add_module(p, torch.nn.Module())
+            m = getattr(m, p)
+        if v.dtype.is_floating_point and not parts[-1].startswith("running_"):
+            m.register_parameter(parts[-1], torch.nn.Parameter(v.clone(), requires_grad=False))
+        else:
+            m.register_buffer(parts[-1], v.clone())
+    torch.jit.save(torch.jit.script(root), path)

@@ -34,6 +34,7 @@ struct Case {
   int bias, act, resid, resid_fp32, mask, colstats;
   float alpha;
   int cpu_check;
+  int heads;  // > 0: two-level batch (outer = batch/heads images, inner = heads, head dim 64 slices of a [L, heads*64] matrix)
 };
 
 static std::vector<Case> make_cases() {
@@ -61,6 +62,10 @@ static std::vector<Case> make_cases() {
   add("nt_K32_N64", 1000, 64, 32, 1, 0, 0);
   add("nt_batched_676x676x64", 676, 676, 64, 5, 0, 0);
   add("nt_batched_17x17x64", 17, 17, 64, 7, 0, 0)->cpu_check = 1;
+  // two-level batch: per-head slices of packed [B, L, heads*64] projections (attention)
+  { auto x = add("heads_qk_100x100x64", 100, 100, 64, 8, 0, 0); x->heads = 4; x->cpu_check = 1; x->alpha = 0.125f; }
+  { auto x = add("heads_pv_100x64x100", 100, 64, 100, 8, 0, 1); x->heads = 4; x->cpu_check = 1; }
+  { auto x = add("heads_dk_100x64x100", 100, 64, 100, 8, 1, 1); x->heads = 4; x->cpu_check = 1; }
   // A K-major, B MN-major (dgrad / P.V / dS.K)
   add("nn_128x128x64", 128, 128, 64, 1, 0, 1)->cpu_check = 1;
   add("nn_300x200x136", 300, 200, 136, 1, 0, 1)->cpu_check = 1;
@@ -158,6 +163,23 @@ static void setup(const Case& cs, Buffers& b) {
   a.d_tap_n = cs.N;
   a.ldd = round8(d_cols) + (cs.tap_mode == 2 ? 0 : 8);
   a.strideD = (long long)cs.M * a.ldd;
+  if (cs.heads > 0) {
+    // operands that are "per-head 64-wide column slices" get inner stride 64; score-like operands stay dense
+    const int H = cs.heads, Bo = cs.batch / H;
+    a.batch_inner = H;
+    auto sliced = [&](bool mn, int inner_dim) { return inner_dim == 64; };
+    // A: K-major -> inner dim K; MN-major -> inner dim M
+    const int a_inner = cs.a_mn ? cs.M : cs.K, a_outer = cs.a_mn ? cs.K : cs.M;
+    if (sliced(cs.a_mn, a_inner)) { a.lda = H * 64; a.strideA2 = 64; a.strideA = (long long)a_outer * a.lda; b.hA.assign((size_t)a.strideA * Bo, __float2bfloat16(0.f)); }
+    else { a.strideA2 = a.strideA; a.strideA = a.strideA2 * H; }
+    const int b_inner = cs.b_mn ? cs.N : cs.K, b_outer = cs.b_mn ? cs.K : cs.N;
+    if (sliced(cs.b_mn, b_inner)) { a.ldb = H * 64; a.strideB2 = 64; a.strideB = (long long)b_outer * a.ldb; b.hB.assign((size_t)a.strideB * Bo, __float2bfloat16(0.f)); }
+    else { a.strideB2 = a.strideB; a.strideB = a.strideB2 * H; }
+    for (auto& v : b.hA) v = __float2bfloat16(frand());
+    for (auto& v : b.hB) v = __float2bfloat16(frand() * 0.5f);
+    if (cs.N == 64) { a.ldd = H * 64; a.strideD2 = 64; a.strideD = (long long)cs.M * a.ldd; b.d_elems = (size_t)a.strideD * Bo; }
+    else { a.strideD2 = a.strideD; a.strideD = a.strideD2 * H; b.d_elems = (size_t)a.strideD * Bo; }
+  } else
   b.d_elems = (size_t)a.strideD * cs.batch;
   const size_t dbytes = b.d_elems * (cs.d_fp32 ? 4 : 2);
   CK(cudaMalloc(&b.dD_tc, dbytes)); CK(cudaMalloc(&b.dD_ref, dbytes));
@@ -198,8 +220,10 @@ static void setup(const Case& cs, Buffers& b) {
 
 static double host_value(const Case& cs, const Buffers& b, int batch, int m, int n, int ztap) {
   const cris_gemm_args& a = b.args;
-  const __nv_bfloat16* A = b.hA.data() + (size_t)batch * a.strideA;
-  const __nv_bfloat16* B = b.hB.data() + (size_t)batch * a.strideB;
+  const int bin = a.batch_inner > 1 ? a.batch_inner : 1;
+  const size_t bi = batch % bin, bo = batch / bin;
+  const __nv_bfloat16* A = b.hA.data() + bo * a.strideA + bi * a.strideA2;
+  const __nv_bfloat16* B = b.hB.data() + bo * a.strideB + bi * a.strideB2;
   const long long a_rows = cs.a_mn ? cs.K : cs.M, b_rows = cs.b_mn ? cs.K : cs.N;
   double acc = 0;
   const int ntl = cs.tap_mode == 1 ? a.taps : 1;
@@ -312,7 +336,8 @@ static int run_case(const Case& cs) {
       int nn = (int)((frand() * 0.5f + 0.5f) * cs.N) % cs.N;
       int zt = (int)((frand() * 0.5f + 0.5f) * taps_z) % taps_z;
       double hv = host_value(cs, b, bt, m, nn, zt);
-      size_t di = (size_t)bt * b.args.strideD + (size_t)m * b.args.ldd + nn + (cs.tap_mode == 2 ? zt * b.args.d_tap_n : 0);
+      const int bin2 = b.args.batch_inner > 1 ? b.args.batch_inner : 1;
+      size_t di = (size_t)(bt / bin2) * b.args.strideD + (size_t)(bt % bin2) * b.args.strideD2 + (size_t)m * b.args.ldd + nn + (cs.tap_mode == 2 ? zt * b.args.d_tap_n : 0);
       md = fmax(md, fabs(hv - rf[di])); mr = fmax(mr, fabs(hv));
     }
     const double htol = (cs.d_fp32 ? 1e-3 : 1.0 / 96) * fmax(mr, 1e-3);
