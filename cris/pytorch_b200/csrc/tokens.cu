@@ -8,19 +8,19 @@
 namespace cris {
 
 // ---- softmax over rows of S[nb][Lq][ld] (scores already scaled by the GEMM alpha) ----------------
-// One warp per row; Lk <= 32*MAXE.  causal: key j > query i masked.  key padding: kpm[b][j] != 0 masked,
-// b = batch_index / heads.  P (bf16) = softmax; Pd (optional) = dropout(P) * 1/(1-p).
+// One warp per row; Lk <= 32*MAXE.  causal: key j > query i masked.  key padding: token id word[b][j] == 0
+// masked (pad_mask of model/segmenter.py:37), b = batch_index / heads.  P (bf16) = softmax; Pd (optional) = dropout(P) * 1/(1-p).
 template <int MAXE>
 __global__ void __launch_bounds__(256)
     softmax_fwd_kernel(const __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ P,
                        __nv_bfloat16* __restrict__ Pd, long long ld, long long batch_stride, int nb, int Lq, int Lk,
-                       int heads, const uint8_t* __restrict__ kpm, int causal, float p_drop, uint64_t seed) {
+                       int heads, const long long* __restrict__ kpm, int causal, float p_drop, uint64_t seed) {
   const int lane = threadIdx.x & 31;
   const long long rid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (rid >= (long long)nb * Lq) return;
   const int bi = (int)(rid / Lq), qi = (int)(rid % Lq);
   const long long off = (long long)bi * batch_stride + (long long)qi * ld;
-  const uint8_t* km = kpm ? kpm + (long long)(bi / heads) * Lk : nullptr;
+  const long long* km = kpm ? kpm + (long long)(bi / heads) * Lk : nullptr;  // token ids; id 0 = padding
   float v[MAXE];
   float mx = -INFINITY;
 #pragma unroll
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256)
     float x = -INFINITY;
     if (j < Lk) {
       x = bf2f(S[off + j]);
-      if ((causal && j > qi) || (km && km[j])) x = -INFINITY;
+      if ((causal && j > qi) || (km && km[j] == 0)) x = -INFINITY;
     }
     v[e] = x;
     mx = fmaxf(mx, x);
@@ -274,7 +274,8 @@ using namespace cris;
 extern "C" {
 
 int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
-                     int heads, const uint8_t* kpm, int causal, float p_drop, uint64_t seed, void* stream) {
+                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, void* stream) {
+  const long long* kpm = reinterpret_cast<const long long*>(kpm_word);
   CRIS_CHECK_ARG(Lk >= 1 && Lk <= 32 * 22, "softmax: Lk=%d out of range (max 704)", Lk);
   const int grid = (int)(((long long)nb * Lq + 7) / 8);
   if (Lk <= 32)

@@ -1,0 +1,1061 @@
+"""The sm_100a execution engine behind `cris.pytorch_b200.CRIS`.
+
+One forward of the reference's `CRIS.forward` (model/segmenter.py:29-62) is a fixed sequence of launches of
+the hand-written kernels in libcris_b200.so over torch-allocated device buffers; the backward replays a tape of
+closures recorded during the forward (a purpose-built reverse-mode pass: PyTorch's autograd only sees one
+`torch.autograd.Function`, so DDP / GradScaler / optimizers of the reference's train.py keep working).
+
+Layout: image activations are bf16 "padded NHWC" row matrices [N*(H+2)*(W+2), C] with a zero border, so that a
+3x3 convolution is 9 row-shifted GEMM taps; token activations are [B*L, C] (bf16, or fp32 for
+the transformer residual streams).  PyTorch is used for memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import GemmArgs, call, gemm
+
+ACT_NONE, ACT_RELU, ACT_QGELU = 0, 1, 2
+TAP_NONE, TAP_ACCUM, TAP_WGRAD = 0, 1, 2
+BN_EPS, LN_EPS, BN_MOMENTUM = 1e-5, 1e-5, 0.1
+
+
+def _r8(x: int) -> int:
+    return (x + 7) // 8 * 8
+
+
+class Mat:
+    """A [rows, C] device matrix view (pitch `ld` elements) over a torch buffer; optional padded-NHWC geometry."""
+    __slots__ = ("buf", "ptr", "rows", "C", "ld", "fp32", "geom", "root", "col0", "gbuf", "gwritten", "need_grad")
+
+    def __init__(self, buf, rows, C, ld=None, fp32=False, geom=None, ptr=None, root=None, col0=0):
+        self.buf, self.rows, self.C = buf, rows, C
+        self.ld = C if ld is None else ld
+        self.fp32, self.geom = fp32, geom
+        self.ptr = buf.data_ptr() if ptr is None else ptr
+        self.root, self.col0 = root, col0
+        self.gbuf: Optional["Mat"] = None
+        self.gwritten = False
+        self.need_grad = True
+
+    @property
+    def esize(self):
+        return 4 if self.fp32 else 2
+
+    def cols(self, c0: int, c1: int) -> "Mat":
+        r = self.root if self.root is not None else self
+        return Mat(self.buf, self.rows, c1 - c0, self.ld, self.fp32, self.geom, self.ptr + c0 * self.esize, r,
+                   self.col0 + c0)
+
+    def rows_slice(self, r0: int, r1: int) -> "Mat":
+        m = Mat(self.buf, r1 - r0, self.C, self.ld, self.fp32, None, self.ptr + r0 * self.ld * self.esize)
+        return m
+
+    @property
+    def hp(self):
+        return self.geom[1] + 2 if self.geom else 0
+
+    @property
+    def wp(self):
+        return self.geom[2] + 2 if self.geom else 0
+
+
+class PackedWeights:
+    """bf16 kernel-layout copies of the fp32 master parameters, refreshed when a parameter's version changes
+    (optimizer steps are in-place): conv 3x3 -> [Cout][9][cin_pad]; 1x1 conv / Linear / in_proj -> [out][in]."""
+
+    def __init__(self):
+        self.cache: Dict[str, tuple] = {}
+
+    def get(self, name: str, p: torch.Tensor) -> Mat:
+        ent = self.cache.get(name)
+        key = (p._version, p.data_ptr())
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        w = p.detach()
+        if w.dim() == 4 and w.shape[2] == 3:
+            cout, cin = w.shape[0], w.shape[1]
+            cp = _r8(cin)
+            buf = ent[1].buf if ent is not None else torch.empty(cout, 9 * cp, dtype=torch.bfloat16, device=w.device)
+            call("cris_pack_conv_weight", w.data_ptr(), buf.data_ptr(), cout, cin, 9, cp)
+            m = Mat(buf, cout, 9 * cp)
+        else:
+            rows = w.shape[0]
+            cols = w.numel() // rows
+            ld = _r8(cols)
+            buf = ent[1].buf if ent is not None else torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+            call("cris_pack_matrix", w.data_ptr(), buf.data_ptr(), rows, cols, ld)
+            m = Mat(buf, rows, cols, ld)
+        self.cache[name] = (key, m)
+        return m
+
+
+def _bicubic_matrix(src: int, H: int, W: int) -> torch.Tensor:
+    """[H*W, src*src] interpolation matrix of F.interpolate(mode='bicubic', align_corners=False) from a
+    src x src grid (model/clip.py:101-104).  Batch-independent constant, built once on the host."""
+    eye = torch.eye(src * src).reshape(src * src, 1, src, src)
+    out = F.interpolate(eye, size=(H, W), mode="bicubic", align_corners=False)  # [s*s, 1, H, W]
+    return out.reshape(src * src, H * W).t().contiguous()
+
+
+def _pos1d(d: int, length: int) -> torch.Tensor:
+    """model/layers.py:106-123 — [length, d] sinusoid table (constant)."""
+    pos = torch.arange(length, dtype=torch.float32)[:, None]
+    freq = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(length, d)
+    pe[:, 0::2] = torch.sin(pos * freq)
+    pe[:, 1::2] = torch.cos(pos * freq)
+    return pe
+
+
+def _pos2d(d: int, H: int, W: int) -> torch.Tensor:
+    """model/layers.py:125-152 — [H*W, d]: first half of the channels encodes w, second half h (constant)."""
+    half = d // 2
+    freq = torch.exp(torch.arange(0.0, half, 2) * -(math.log(10000.0) / half))
+    pw = torch.arange(0.0, W)[:, None] * freq
+    ph = torch.arange(0.0, H)[:, None] * freq
+    pe = torch.zeros(H, W, d)
+    pe[:, :, 0:half:2] = torch.sin(pw)[None]
+    pe[:, :, 1:half:2] = torch.cos(pw)[None]
+    pe[:, :, half::2] = torch.sin(ph)[:, None]
+    pe[:, :, half + 1::2] = torch.cos(ph)[:, None]
+    return pe.reshape(H * W, d)
+
+
+def mat_to_torch(m: Mat) -> torch.Tensor:
+    """Debug/test helper: copy a Mat out as fp32 — NCHW for padded-NHWC image tensors, [rows, C] otherwise."""
+    esz = m.esize
+    flat = m.buf.reshape(-1)
+    off = (m.ptr - m.buf.data_ptr()) // esz
+    t = torch.as_strided(flat, (m.rows, m.C), (m.ld, 1), off).float()
+    if m.geom is not None:
+        N, H, W = m.geom
+        t = t.reshape(N, H + 2, W + 2, m.C)[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).contiguous()
+    return t
+
+
+class Engine:
+    def __init__(self, model: nn.Module):
+        self.model = model
+        self.packed = PackedWeights()
+        self.consts: Dict[tuple, torch.Tensor] = {}
+        self.step = 0
+        self.debug_taps: Optional[dict] = None  # set to {} to collect named intermediates (tests only)
+        _lib.lib()
+
+    def const(self, key, fn, device):
+        t = self.consts.get(key)
+        if t is None or t.device != device:
+            t = fn().to(device)
+            self.consts[key] = t
+        return t
+
+    # -------------------------------------------------------------------------------------------
+    def run(self, img, word, mask):
+        model = self.model
+        training = model.training
+        if training and mask is None:
+            raise ValueError("CRIS.forward in training mode needs the mask (model/segmenter.py:54-59)")
+        _lib.device_check()
+        if training and torch.is_grad_enabled():
+            names, params = [], []
+            for k, p in model.named_parameters():
+                if k == "backbone.logit_scale":  # never used by the path
+                    continue
+                names.append(k)
+                params.append(p)
+            pred, mask_r, loss = _CRISFunction.apply(self, names, img, word, mask, *params)
+            return pred, mask_r, loss
+        with torch.no_grad():
+            r = Run(self, img, word, mask, training, record=False)
+            r.forward()
+        if training:
+            return r.pred, r.mask_out, r.loss
+        return r.pred
+
+
+class _CRISFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, names, img, word, mask, *params):
+        r = Run(engine, img, word, mask, True, record=True)
+        r.forward()
+        ctx.run = r
+        ctx.names = names
+        ctx.mark_non_differentiable(r.pred, r.mask_out)
+        return r.pred, r.mask_out, r.loss
+
+    @staticmethod
+    def backward(ctx, _dpred, _dmask, dloss):
+        r: Run = ctx.run
+        grads = r.backward(dloss, ctx.names)
+        ctx.run = None
+        return (None, None, None, None, None, *grads)
+
+
+class Run:
+    """State of one forward (+ backward) pass."""
+
+    def __init__(self, engine: Engine, img, word, mask, training: bool, record: bool):
+        self.e = engine
+        self.model = engine.model
+        self.dev = img.device
+        self.img = img.contiguous().float()
+        self.word = word.contiguous().long()
+        self.mask = None if mask is None else mask.contiguous().float()
+        self.training = training
+        self.record = record
+        self.tape: List = []
+        self.P = dict(self.model.named_parameters())
+        self.Bf = dict(self.model.named_buffers())
+        self.pgrad: Dict[str, torch.Tensor] = {}
+        self.p_drop = float(self.model.dropout_p) if training else 0.0
+        engine.step += 1
+        self.seed_base = (torch.initial_seed() * 1000003 + engine.step * 7919) & ((1 << 62) - 1)
+        self.n_seed = 0
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.sync_bn = training and self.world > 1 and any(
+            isinstance(m, nn.SyncBatchNorm) for m in self.model.modules())
+
+    # ---- small helpers -------------------------------------------------------------------------
+    def new(self, rows, C, fp32=False, geom=None, zero=False, ld=None) -> Mat:
+        ld = C if ld is None else ld
+        dt = torch.float32 if fp32 else torch.bfloat16
+        buf = (torch.zeros if zero else torch.empty)(rows, ld, dtype=dt, device=self.dev)
+        return Mat(buf, rows, C, ld, fp32, geom)
+
+    def padded(self, N, H, W, C, zero=False, ld=None) -> Mat:
+        return self.new(N * (H + 2) * (W + 2), C, False, (N, H, W), zero, ld)
+
+    def f32(self, n, zero=False):
+        return (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.dev)
+
+    def tap(self, name: str, m: Mat):
+        if self.e.debug_taps is not None:
+            self.e.debug_taps[name] = mat_to_torch(m)
+
+    def seed(self):
+        self.n_seed += 1
+        return (self.seed_base + self.n_seed * 104729) & ((1 << 63) - 1)
+
+    def w(self, name) -> Mat:
+        return self.e.packed.get(name, self.P[name])
+
+    def pg(self, name) -> torch.Tensor:
+        g = self.pgrad.get(name)
+        if g is None:
+            g = torch.zeros_like(self.P[name], dtype=torch.float32)
+            self.pgrad[name] = g
+        return g
+
+    def on_backward(self, fn):
+        if self.record:
+            self.tape.append(fn)
+
+    # gradient slots ---------------------------------------------------------------------------
+    def grad_slot(self, m: Mat):
+        """-> (grad Mat, accumulate?) for the tensor `m`; handles column slices of concat buffers."""
+        root = m.root if m.root is not None else m
+        if root.gbuf is None:
+            whole = m.root is None
+            g = self.new(root.rows, root.C, root.fp32, root.geom, zero=not whole, ld=None)
+            root.gbuf = g
+            root.gwritten = True
+            if whole:
+                return g, False
+            return g.cols(m.col0, m.col0 + m.C), True
+        g = root.gbuf
+        if m.root is None:
+            return g, True
+        return g.cols(m.col0, m.col0 + m.C), True
+
+    def grad_of(self, m: Mat) -> Optional[Mat]:
+        root = m.root if m.root is not None else m
+        if root.gbuf is None:
+            return None
+        return root.gbuf if m.root is None else root.gbuf.cols(m.col0, m.col0 + m.C)
+
+    def set_grad(self, m: Mat, g: Mat):
+        assert m.root is None
+        m.gbuf = g
+        m.gwritten = True
+
+    # ---- kernel wrappers ----------------------------------------------------------------------------
+    def ew(self, op, a: Optional[Mat], b: Optional[Mat], out: Mat, p=0.0, seed=0):
+        ref = a if a is not None else b
+        call("cris_elementwise", op, a.ptr if a else None, int(a.fp32) if a else 0, a.ld if a else 0,
+             b.ptr if b else None, int(b.fp32) if b else 0, b.ld if b else 0, out.ptr, int(out.fp32), out.ld,
+             ref.rows, ref.C, float(p), int(seed))
+
+    def accumulate_into(self, src: Mat, dst_owner: Mat):
+        """grad(dst_owner) (+)= src"""
+        slot, acc = self.grad_slot(dst_owner)
+        self.ew(0, src, slot if acc else None, slot)
+
+    def gemm(self, A: Mat, B: Mat, D: Mat, M, N, K, *, a_mn=0, b_mn=0, batch=1, batch_inner=1, sA=(0, 0), sB=(0, 0),
+             sD=(0, 0), alpha=1.0, bias=None, act=0, resid: Optional[Mat] = None, sR=(0, 0), mask_geom=None,
+             colstats=None, tap_mode=0, taps=1, tap_off=None, b_tap_k=0, b_tap_n=0, d_tap_n=0, splits=1,
+             accumulate=0, d_col_stride=0, a_rows=0, b_rows=0):
+        g = GemmArgs()
+        g.A, g.lda, g.strideA, g.strideA2 = A.ptr, A.ld, sA[0], sA[1]
+        g.B, g.ldb, g.strideB, g.strideB2 = B.ptr, B.ld, sB[0], sB[1]
+        g.D, g.ldd, g.strideD, g.strideD2 = D.ptr, D.ld, sD[0], sD[1]
+        g.M, g.N, g.K, g.batch, g.batch_inner = M, N, K, batch, batch_inner
+        g.a_mn, g.b_mn, g.d_fp32, g.accumulate = a_mn, b_mn, int(D.fp32), accumulate
+        g.tap_mode, g.taps = tap_mode, taps
+        if tap_off is not None:
+            for i, v in enumerate(tap_off):
+                g.tap_off[i] = v
+        g.b_tap_k, g.b_tap_n, g.d_tap_n, g.splits = b_tap_k, b_tap_n, d_tap_n, splits
+        g.alpha = alpha
+        g.bias = bias
+        g.act = act
+        if resid is not None:
+            g.resid, g.ldr, g.strideR, g.strideR2, g.resid_fp32 = resid.ptr, resid.ld, sR[0], sR[1], int(resid.fp32)
+        if mask_geom is not None:
+            g.mask_hp, g.mask_wp = mask_geom[1] + 2, mask_geom[2] + 2
+        g.colstats = colstats
+        g.a_rows, g.b_rows, g.d_col_stride = a_rows, b_rows, d_col_stride
+        gemm(g)
+
+    @staticmethod
+    def taps_of(geom):
+        wp = geom[2] + 2
+        return [dy * wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+    @staticmethod
+    def wgrad_splits(m_tiles, n_tiles, taps, K):
+        tiles = m_tiles * n_tiles * taps
+        nkb = (K + 63) // 64
+        return max(1, min(nkb, (2 * 148 + tiles - 1) // tiles))
+
+    def col_sum(self, m: Mat, width: int, hp=0, wp=0) -> torch.Tensor:
+        """per-column sums of m[:, :width] (bias gradients); fp32 vector of the padded width."""
+        wpad = _r8(width)
+        out = self.f32(wpad)
+        nb = max(1, min(592, m.rows // 64))
+        for c0 in range(0, wpad, 2048):
+            cw = min(2048, wpad - c0)
+            pt = self.f32(nb * 2 * cw)
+            call("cris_col_reduce", 2, m.ptr + c0 * m.esize, m.ld, int(m.fp32), None, 0, None, 0, None, 0, 0, None, None,
+                 m.rows, cw, 0, hp, wp, pt.data_ptr(), nb)
+            sm = self.f32(2 * cw)
+            call("cris_bn_reduce_partials", pt.data_ptr(), nb, cw, sm.data_ptr())
+            out[c0:c0 + cw].copy_(sm[:cw])
+        return out
+
+    # ---- BatchNorm ---------------------------------------------------------------------------------
+    def allreduce(self, t: torch.Tensor):
+        dist.all_reduce(t)
+
+    def bn_forward(self, z: Mat, prefix: str, relu: bool, resid: Optional[Mat] = None, out: Optional[Mat] = None,
+                   partials=None, n_tiles=0) -> Mat:
+        """BatchNorm over the rows of z (+ residual, ReLU).  Training = batch statistics (SyncBN-equivalent
+        across ranks), eval = running statistics.  Reference: nn.BatchNorm2d/1d call sites in model/clip.py,
+        model/layers.py; SyncBatchNorm (train.py:97-98)."""
+        C = z.C
+        gamma, beta = self.P[prefix + ".weight"], self.P[prefix + ".bias"]
+        rm, rv = self.Bf[prefix + ".running_mean"], self.Bf[prefix + ".running_var"]
+        coef = self.f32(4 * C)  # scale | shift | mean | invstd
+        count_local = z.geom[0] * z.geom[1] * z.geom[2] if z.geom else z.rows
+        count = float(count_local * (self.world if self.sync_bn else 1))
+        sums = None
+        if self.training:
+            if partials is None:
+                n_tiles = max(1, min(592, z.rows // 64))
+                partials = self.f32(n_tiles * 2 * C)
+                call("cris_col_reduce", 0, z.ptr, z.ld, 0, None, 0, None, 0, None, 0, 0, None, None, z.rows, C, 0,
+                     z.hp, z.wp, partials.data_ptr(), n_tiles)
+            sums = self.f32(2 * C)
+            call("cris_bn_reduce_partials", partials.data_ptr(), n_tiles, C, sums.data_ptr())
+            if self.sync_bn:
+                self.allreduce(sums)
+            call("cris_bn_coeffs", sums.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM,
+                 rm.data_ptr(), rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * C, coef.data_ptr() + 8 * C,
+                 coef.data_ptr() + 12 * C, C, 1)
+            nbt = self.Bf.get(prefix + ".num_batches_tracked")
+            if nbt is not None:
+                nbt.add_(1)
+        else:
+            call("cris_bn_coeffs", None, 1.0, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(),
+                 rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * C, coef.data_ptr() + 8 * C,
+                 coef.data_ptr() + 12 * C, C, 0)
+        y = out if out is not None else self.new(z.rows, C, False, z.geom)
+        call("cris_bn_apply", z.ptr, z.ld, coef.data_ptr(), coef.data_ptr() + 4 * C, resid.ptr if resid else None,
+             resid.ld if resid else 0, y.ptr, y.ld, z.rows, C, int(relu), z.hp, z.wp)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            nb = max(1, min(592, z.rows // 64))
+            part = self.f32(nb * 2 * C)
+            call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, y.ptr, y.ld, z.ptr, z.ld, 0, coef.data_ptr() + 8 * C,
+                 coef.data_ptr() + 12 * C, z.rows, C, int(relu), z.hp, z.wp, part.data_ptr(), nb)
+            bs = self.f32(2 * C)
+            call("cris_bn_reduce_partials", part.data_ptr(), nb, C, bs.data_ptr())
+            # parameter gradients are LOCAL sums (DDP averages them), dx needs the GLOBAL sums
+            gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
+            call("cris_elementwise", 0, bs.data_ptr(), 1, C, None, 0, 0, gb.data_ptr(), 1, C, 1, C, 0.0, 0)
+            call("cris_elementwise", 0, bs.data_ptr() + 4 * C, 1, C, None, 0, 0, gg.data_ptr(), 1, C, 1, C, 0.0, 0)
+            if self.sync_bn:
+                self.allreduce(bs)
+            dz = self.new(z.rows, C, False, z.geom)
+            dres_ptr, dres_ld, dres_acc = None, 0, 0
+            if resid is not None and resid.need_grad:
+                slot, acc = self.grad_slot(resid)
+                dres_ptr, dres_ld, dres_acc = slot.ptr, slot.ld, int(acc)
+            call("cris_bn_bwd_apply", dy.ptr, dy.ld, y.ptr, y.ld, z.ptr, z.ld, coef.data_ptr() + 8 * C,
+                 coef.data_ptr() + 12 * C, gamma.data_ptr(), bs.data_ptr(), count, dz.ptr, dz.ld, dres_ptr, dres_ld,
+                 dres_acc, z.rows, C, int(relu), z.hp, z.wp)
+            self.set_grad(z, dz)
+
+        if self.training:
+            self.on_backward(bwd)
+        return y
+
+    # ---- convolution (implicit GEMM on tcgen05) ---------------------------------------------------
+    def conv(self, x: Mat, wname: str, k: int, stats: bool, bias_name: Optional[str] = None,
+             cin: Optional[int] = None):
+        """z = conv_kxk(x) (stride 1, zero padding k//2), optional bias; returns (z, colstats partials, tiles)."""
+        wp = self.w(wname)
+        Wt = self.P[wname]
+        cout = Wt.shape[0]
+        cin = Wt.shape[1] if cin is None else cin
+        cin_pad = _r8(Wt.shape[1])
+        z = self.new(x.rows, cout, False, x.geom)
+        n_tiles = (x.rows + 127) // 128
+        part = self.f32(n_tiles * 2 * cout) if stats else None
+        bias = self.P[bias_name].data_ptr() if bias_name else None
+        offs = self.taps_of(x.geom) if k == 3 else None
+        self.gemm(x, wp, z, x.rows, cout, cin, bias=bias, mask_geom=x.geom,
+                  colstats=part.data_ptr() if stats else None, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE,
+                  taps=9 if k == 3 else 1, tap_off=offs, b_tap_k=cin_pad if k == 3 else 0)
+
+        def bwd():
+            dz = self.grad_of(z)
+            if dz is None:
+                return
+            if bias_name:
+                self.pg(bias_name).copy_(self.col_sum(dz, cout, z.hp, z.wp)[:cout])
+            # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
+            gw = self.pg(wname)
+            gwm = Mat(gw, cout, Wt.shape[1] * (9 if k == 3 else 1), fp32=True)
+            splits = self.wgrad_splits((cout + 127) // 128, (cin + 127) // 128, 9 if k == 3 else 1, x.rows)
+            if k == 3:
+                self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
+                          d_tap_n=1, d_col_stride=9, splits=splits, accumulate=1)
+            else:
+                self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, splits=splits, accumulate=1)
+            # dgrad: dx[row] = sum_tap dz[row - off_tap] * W_tap
+            if x.need_grad:
+                slot, acc = self.grad_slot(x)
+                n_in = min(cin, x.C)
+                self.gemm(dz, wp, slot, x.rows, n_in, cout, b_mn=1, mask_geom=x.geom, resid=slot if acc else None,
+                          tap_mode=TAP_ACCUM if k == 3 else TAP_NONE, taps=9 if k == 3 else 1,
+                          tap_off=[-o for o in offs] if k == 3 else None, b_tap_n=cin_pad if k == 3 else 0,
+                          b_rows=cout)
+
+        if self.training:
+            self.on_backward(bwd)
+        return z, part, n_tiles
+
+    def conv_bn(self, x: Mat, conv_name: str, bn_prefix: str, k: int, relu=True, resid=None, out=None, cin=None):
+        z, part, nt = self.conv(x, conv_name, k, stats=self.training, cin=cin)
+        return self.bn_forward(z, bn_prefix, relu, resid, out, part, nt)
+
+    # ---- resampling -------------------------------------------------------------------------------
+    def avgpool(self, x: Mat, out: Optional[Mat] = None) -> Mat:
+        N, H, W = x.geom
+        y = out if out is not None else self.padded(N, H // 2, W // 2, x.C)
+        y.geom = (N, H // 2, W // 2)
+        call("cris_avgpool2_fwd", x.ptr, x.ld, y.ptr, y.ld, N, H, W, x.C)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None or not x.need_grad:
+                return
+            slot, acc = self.grad_slot(x)
+            call("cris_avgpool2_bwd", dy.ptr, dy.ld, slot.ptr, slot.ld, int(acc), N, H, W, x.C)
+
+        if self.training:
+            self.on_backward(bwd)
+        return y
+
+    def upsample(self, x: Mat, out: Optional[Mat] = None) -> Mat:
+        N, H, W = x.geom
+        y = out if out is not None else self.padded(N, 2 * H, 2 * W, x.C)
+        call("cris_upsample2x_fwd", x.ptr, x.ld, y.ptr, y.ld, N, H, W, x.C)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None or not x.need_grad:
+                return
+            slot, acc = self.grad_slot(x)
+            call("cris_upsample2x_bwd", dy.ptr, dy.ld, slot.ptr, slot.ld, int(acc), N, H, W, x.C)
+
+        if self.training:
+            self.on_backward(bwd)
+        return y
+
+    # ---- token-side building blocks -----------------------------------------------------------------
+    def linear(self, x: Mat, wname: str, bname: Optional[str], *, act=ACT_NONE, out_fp32=False, w_rows=None,
+               stats=False, transposed_weight=False, out: Optional[Mat] = None):
+        """y = act(x @ W^T + b) (nn.Linear / 1x1 projections of MHA).  `w_rows=(r0, r1)` uses a row slice of the
+        weight (packed in_proj of nn.MultiheadAttention).  transposed_weight: W is stored [in, out]
+        (CLIP text_projection, model/clip.py:451-452)."""
+        Wt = self.P[wname]
+        wp = self.w(wname)
+        if transposed_weight:
+            n_in, n_out = Wt.shape
+            r0, r1 = 0, n_out
+            wv = wp
+        else:
+            r0, r1 = (0, Wt.shape[0]) if w_rows is None else w_rows
+            n_out, n_in = r1 - r0, Wt.shape[1]
+            wv = wp.rows_slice(r0, r1)
+        bias_ptr = (self.P[bname].data_ptr() + 4 * r0) if bname else None
+        y = out if out is not None else self.new(x.rows, n_out, out_fp32, None, ld=_r8(n_out))
+        n_tiles = (x.rows + 127) // 128
+        part = self.f32(n_tiles * 2 * n_out) if stats else None
+        self.gemm(x, wv, y, x.rows, n_out, n_in, b_mn=1 if transposed_weight else 0, bias=bias_ptr, act=act,
+                  colstats=part.data_ptr() if stats else None, b_rows=n_in if transposed_weight else 0)
+
+        def bwd():
+            dy = self.grad_of(y)
+            if dy is None:
+                return
+            if act == ACT_RELU:
+                t = self.new(y.rows, y.C, False, None, ld=y.ld)
+                self.ew(5, y, dy, t)
+                dy = t
+            elif dy.fp32:
+                # bf16 copy for the tensor-core GEMMs; odd widths (proj.txt: 9C+1) are cast over the padded pitch
+                wpad = _r8(y.C)
+                t = self.new(y.rows, y.C, False, None, ld=wpad)
+                self.ew(0, Mat(dy.buf, dy.rows, wpad, dy.ld, True, ptr=dy.ptr), None, Mat(t.buf, t.rows, wpad, wpad))
+                dy = t
+            if bname:
+                sm = self.col_sum(dy, n_out)
+                self.pg(bname)[r0:r1].copy_(sm[:n_out])
+            gw = self.pg(wname)
+            if transposed_weight:
+                gwm = Mat(gw, n_in, n_out, fp32=True)
+                sp = self.wgrad_splits((n_in + 127) // 128, (n_out + 127) // 128, 1, x.rows)
+                self.gemm(x, dy, gwm, n_in, n_out, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
+            else:
+                gwm = Mat(gw, n_out, n_in, fp32=True, ptr=gw.data_ptr() + 4 * r0 * n_in)
+                sp = self.wgrad_splits((n_out + 127) // 128, (n_in + 127) // 128, 1, x.rows)
+                self.gemm(dy, x, gwm, n_out, n_in, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
+            if x.need_grad:
+                slot, acc = self.grad_slot(x)
+                if slot.fp32:
+                    raise RuntimeError("linear input gradients are bf16")
+                self.gemm(dy, wv, slot, x.rows, n_in, n_out, b_mn=0 if transposed_weight else 1,
+                          resid=slot if acc else None, b_rows=0 if transposed_weight else n_out)
+
+        if self.training:
+            self.on_backward(bwd)
+        return (y, part, n_tiles) if stats else y
+
+    def layernorm(self, x: Mat, prefix: str, add: Optional[torch.Tensor] = None, want_y=True, want_y2=False):
+        """y = LN(x) (bf16); y2 = y + add[row % period] (bf16) — nn.LayerNorm (+ with_pos_embed,
+        model/layers.py:221-222)."""
+        C = x.C
+        gamma, beta = self.P[prefix + ".weight"], self.P[prefix + ".bias"]
+        y = self.new(x.rows, C) if want_y else None
+        y2 = self.new(x.rows, C) if want_y2 else None
+        stats = self.f32(2 * x.rows)
+        call("cris_layernorm_fwd", x.ptr, int(x.fp32), x.ld, gamma.data_ptr(), beta.data_ptr(),
+             add.data_ptr() if add is not None else None, C, add.shape[0] if add is not None else 1,
+             y.ptr if y else None, 0, C, y2.ptr if y2 else None, C, stats.data_ptr(), stats.data_ptr() + 4 * x.rows,
+             x.rows, C, LN_EPS)
+
+        def bwd():
+            d1 = self.grad_of(y) if y is not None else None
+            d2 = self.grad_of(y2) if y2 is not None else None
+            if d1 is None and d2 is None:
+                return
+            if d1 is None:
+                d1, d2 = d2, None
+            nb = max(1, min(592, x.rows // 64))
+            pt = self.f32(nb * 2 * C)
+            call("cris_col_reduce", 3, d1.ptr, d1.ld, int(d1.fp32), d2.ptr if d2 else None, d2.ld if d2 else 0, None, 0,
+                 x.ptr, x.ld, int(x.fp32), stats.data_ptr(), stats.data_ptr() + 4 * x.rows, x.rows, C, 0, 0, 0,
+                 pt.data_ptr(), nb)
+            sm = self.f32(2 * C)
+            call("cris_bn_reduce_partials", pt.data_ptr(), nb, C, sm.data_ptr())
+            gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
+            call("cris_elementwise", 0, sm.data_ptr(), 1, C, None, 0, 0, gb.data_ptr(), 1, C, 1, C, 0.0, 0)
+            call("cris_elementwise", 0, sm.data_ptr() + 4 * C, 1, C, None, 0, 0, gg.data_ptr(), 1, C, 1, C, 0.0, 0)
+            if x.need_grad:
+                slot, acc = self.grad_slot(x)
+                call("cris_layernorm_bwd", d1.ptr, int(d1.fp32), d1.ld, d2.ptr if d2 else None, d2.ld if d2 else 0,
+                     x.ptr, int(x.fp32), x.ld, gamma.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * x.rows,
+                     slot.ptr, int(slot.fp32), slot.ld, int(acc), x.rows, C)
+
+        if self.training:
+            self.on_backward(bwd)
+        return y, y2
+
+    def residual_add(self, x: Mat, h: Mat, p: float) -> Mat:
+        """x_new = x + dropout(h) on the fp32 residual stream (model/layers.py:237,245,249; clip.py:263-264)."""
+        out = self.new(x.rows, x.C, True)
+        sd = self.seed() if p > 0 else 0
+        self.ew(1, x, h, out, p, sd)
+
+        def bwd():
+            g = self.grad_of(out)
+            if g is None:
+                return
+            # identity branch: grad(x) (+)= g ; dropout branch: grad(h) (+)= dropout_mask(g)
+            slot, acc = self.grad_slot(h)
+            if acc:
+                t = self.new(h.rows, h.C, slot.fp32)
+                self.ew(2, g, None, t, p, sd)
+                self.ew(0, slot, t, slot)
+            else:
+                self.ew(2, g, None, slot, p, sd)
+            slot, acc = self.grad_slot(x)
+            self.ew(0, g, slot if acc else None, slot)
+
+        if self.training:
+            self.on_backward(bwd)
+        return out
+
+    def attention(self, q: Mat, k: Mat, v: Mat, B, heads, Lq, Lk, causal=False, key_pad=False, p_drop=0.0) -> Mat:
+        """softmax(q k^T / sqrt(64) + masks) v per head (core of F.multi_head_attention_forward as called at
+        model/clip.py:119-139,255-260 and model/layers.py:235,240-243).  q,k,v: [B*L, heads*64] bf16 (possibly
+        column slices of a packed projection)."""
+        E = heads * 64
+        Lkp = _r8(Lk)
+        nb = B * heads
+        S = self.new(nb * Lq, Lk, False, None, ld=Lkp)
+        sS = (heads * Lq * Lkp, Lq * Lkp)
+        alpha = 1.0 / 8.0
+        self.gemm(q, k, S, Lq, Lk, 64, batch=nb, batch_inner=heads, sA=(Lq * q.ld, 64), sB=(Lk * k.ld, 64), sD=sS,
+                  alpha=alpha)
+        Pd = self.new(nb * Lq, Lk, False, None, ld=Lkp) if p_drop > 0 else None
+        sd = self.seed() if p_drop > 0 else 0
+        call("cris_softmax_fwd", S.ptr, S.ptr, Pd.ptr if Pd else None, Lkp, Lq * Lkp, nb, Lq, Lk, heads,
+             self.word.data_ptr() if key_pad else None, int(causal), float(p_drop), int(sd))
+        Puse = Pd if Pd is not None else S
+        o = self.new(B * Lq, E)
+        self.gemm(Puse, v, o, Lq, 64, Lk, b_mn=1, batch=nb, batch_inner=heads, sA=sS, sB=(Lk * v.ld, 64),
+                  sD=(Lq * E, 64), b_rows=Lk)
+
+        def bwd():
+            do = self.grad_of(o)
+            if do is None:
+                return
+            dP = self.new(nb * Lq, Lk, False, None, ld=Lkp)
+            self.gemm(do, v, dP, Lq, Lk, 64, batch=nb, batch_inner=heads, sA=(Lq * do.ld, 64), sB=(Lk * v.ld, 64),
+                      sD=sS)
+            # dV = Pd^T do
+            slot, acc = self.grad_slot(v)
+            self.gemm(Puse, do, slot, Lk, 64, Lq, a_mn=1, b_mn=1, batch=nb, batch_inner=heads, sA=sS,
+                      sB=(Lq * do.ld, 64), sD=(Lk * slot.ld, 64), resid=slot if acc else None,
+                      sR=(Lk * slot.ld, 64), a_rows=Lq, b_rows=Lq)
+            call("cris_softmax_bwd", S.ptr, dP.ptr, Lkp, Lq * Lkp, nb, Lq, Lk, float(p_drop), int(sd))
+            slot, acc = self.grad_slot(q)
+            self.gemm(dP, k, slot, Lq, 64, Lk, b_mn=1, batch=nb, batch_inner=heads, sA=sS, sB=(Lk * k.ld, 64),
+                      sD=(Lq * slot.ld, 64), alpha=alpha, resid=slot if acc else None, sR=(Lq * slot.ld, 64),
+                      b_rows=Lk)
+            slot, acc = self.grad_slot(k)
+            self.gemm(dP, q, slot, Lk, 64, Lq, a_mn=1, b_mn=1, batch=nb, batch_inner=heads, sA=sS,
+                      sB=(Lq * q.ld, 64), sD=(Lk * slot.ld, 64), alpha=alpha, resid=slot if acc else None,
+                      sR=(Lk * slot.ld, 64), a_rows=Lq, b_rows=Lq)
+
+        if self.training:
+            self.on_backward(bwd)
+        return o
+
+    # =================================================================================================
+    # the model
+    # =================================================================================================
+    def forward(self):
+        c3, c4, c5 = self.encode_image()
+        wfeat, state = self.encode_text()
+        fq = self.fpn(c3, c4, c5, state)
+        fq = self.decoder(fq, wfeat)
+        self.projector_and_loss(fq, state)
+
+    # ---- image encoder: model/clip.py:207-223 ------------------------------------------------------------
+    def encode_image(self):
+        v = "backbone.visual"
+        B, _, Hin, Win = self.img.shape
+        if Hin % 32 or Win % 32:
+            raise ValueError("image size must be a multiple of 32")
+        w1 = self.P[v + ".conv1.weight"]
+        c1 = w1.shape[0]
+        z = self.padded(B, Hin // 2, Win // 2, c1)
+        call("cris_stem_conv1_fwd", self.img.data_ptr(), w1.data_ptr(), z.ptr, z.ld, B, Hin, Win, c1)
+        z.need_grad = True
+
+        def bwd_stem():
+            dz = self.grad_of(z)
+            if dz is None:
+                return
+            gw = self.pg(v + ".conv1.weight")
+            call("cris_stem_conv1_wgrad", self.img.data_ptr(), dz.ptr, dz.ld, gw.data_ptr(), B, Hin, Win, c1)
+
+        if self.training:
+            self.on_backward(bwd_stem)
+        x = self.bn_forward(z, v + ".bn1", True)
+        x = self.conv_bn(x, v + ".conv2.weight", v + ".bn2", 3)
+        x = self.conv_bn(x, v + ".conv3.weight", v + ".bn3", 3)
+        x = self.avgpool(x)
+        self.tap("stem", x)
+        feats = []
+        vis = self.model.backbone.visual
+        for li in (1, 2, 3, 4):
+            layer = getattr(vis, f"layer{li}")
+            for bi, blk in enumerate(layer):
+                x = self.bottleneck(x, f"{v}.layer{li}.{bi}", blk.stride, blk.downsample is not None)
+            feats.append(x)
+            self.tap(f"layer{li}", x)
+        c5 = self.attnpool(feats[3], v + ".attnpool", vis.attnpool.num_heads)
+        self.tap("attnpool", c5)
+        return feats[1], feats[2], c5
+
+    def bottleneck(self, x: Mat, p: str, stride: int, has_down: bool) -> Mat:
+        """model/clip.py:44-57."""
+        o = self.conv_bn(x, p + ".conv1.weight", p + ".bn1", 1)
+        o = self.conv_bn(o, p + ".conv2.weight", p + ".bn2", 3)
+        if stride > 1:
+            o = self.avgpool(o)
+        if has_down:
+            idn = self.avgpool(x) if stride > 1 else x
+            idn = self.conv_bn(idn, p + ".downsample.0.weight", p + ".downsample.1", 1, relu=False)
+        else:
+            idn = x
+        return self.conv_bn(o, p + ".conv3.weight", p + ".bn3", 1, relu=True, resid=idn)
+
+    def attnpool(self, x: Mat, p: str, heads: int) -> Mat:
+        """model/clip.py:110-144."""
+        B, H, W = x.geom
+        E = x.C
+        T = H * W
+        zc, part, nt = self.conv(x, p + ".connect.0.weight", 1, stats=self.training)
+        pos = self.P[p + ".positional_embedding"]
+        sp = int(round(math.sqrt(pos.shape[0] - 1)))
+        R = self.e.const(("bicubic", sp, H, W), lambda: _bicubic_matrix(sp, H, W), self.dev)
+        posr = self.f32(T * E)
+        call("cris_small_matmul", R.data_ptr(), pos.data_ptr() + 4 * E, posr.data_ptr(), T, sp * sp, E, 0, 0)
+        tok = self.new(B * T, E)
+        call("cris_padded_to_tokens", x.ptr, x.ld, posr.data_ptr(), E, tok.ptr, 0, tok.ld, B, H, W, E)
+
+        def bwd_tok():
+            dt = self.grad_of(tok)
+            if dt is None:
+                return
+            dposr = self.f32(T * E)
+            call("cris_batch_reduce", dt.ptr, 0, dt.ld, dposr.data_ptr(), E, B, T, E, 0)
+            gp = self.pg(p + ".positional_embedding")
+            call("cris_small_matmul", R.data_ptr(), dposr.data_ptr(), gp.data_ptr() + 4 * E, T, sp * sp, E, 1, 0)
+            slot, acc = self.grad_slot(x)
+            if acc:
+                t = self.padded(B, H, W, E)
+                call("cris_tokens_to_padded", dt.ptr, 0, dt.ld, t.ptr, t.ld, B, H, W, E)
+                self.ew(0, slot, t, slot)
+            else:
+                call("cris_tokens_to_padded", dt.ptr, 0, dt.ld, slot.ptr, slot.ld, B, H, W, E)
+
+        if self.training:
+            self.on_backward(bwd_tok)
+        # k_proj, q_proj, v_proj are adjacent Linear layers -> three GEMMs over the same token matrix
+        qkv = self.new(B * T, 3 * E)
+        k = self.linear(tok, p + ".k_proj.weight", p + ".k_proj.bias", out=qkv.cols(0, E))
+        q = self.linear(tok, p + ".q_proj.weight", p + ".q_proj.bias", out=qkv.cols(E, 2 * E))
+        vv = self.linear(tok, p + ".v_proj.weight", p + ".v_proj.bias", out=qkv.cols(2 * E, 3 * E))
+        o = self.attention(q, k, vv, B, heads, T, T)
+        o = self.linear(o, p + ".c_proj.weight", p + ".c_proj.bias")
+        Co = o.C
+        op = self.padded(B, H, W, Co)
+        call("cris_tokens_to_padded", o.ptr, 0, o.ld, op.ptr, op.ld, B, H, W, Co)
+
+        def bwd_op():
+            g = self.grad_of(op)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(o)
+            assert not acc
+            call("cris_padded_to_tokens", g.ptr, g.ld, None, 0, slot.ptr, 0, slot.ld, B, H, W, Co)
+
+        if self.training:
+            self.on_backward(bwd_op)
+        return self.bn_forward(zc, p + ".connect.1", True, resid=op, partials=part, n_tiles=nt)
+
+    # ---- text encoder: model/clip.py:439-456 ---------------------------------------------------------------
+    def encode_text(self):
+        b = "backbone"
+        B, L = self.word.shape
+        table = self.P[b + ".token_embedding.weight"]
+        pos = self.P[b + ".positional_embedding"]
+        E = table.shape[1]
+        heads = E // 64
+        x = self.new(B * L, E, True)
+        call("cris_embed_fwd", self.word.data_ptr(), table.data_ptr(), pos.data_ptr(), x.ptr, B, L, E)
+
+        def bwd_embed():
+            g = self.grad_of(x)
+            if g is None:
+                return
+            call("cris_embed_bwd", self.word.data_ptr(), g.ptr, self.pg(b + ".token_embedding.weight").data_ptr(),
+                 self.pg(b + ".positional_embedding").data_ptr(), B, L, E)
+
+        if self.training:
+            self.on_backward(bwd_embed)
+        nblk = len(self.model.backbone.transformer.resblocks)
+        for i in range(nblk):
+            p = f"{b}.transformer.resblocks.{i}"
+            h, _ = self.layernorm(x, p + ".ln_1")
+            qkv = self.linear(h, p + ".attn.in_proj_weight", p + ".attn.in_proj_bias")
+            o = self.attention(qkv.cols(0, E), qkv.cols(E, 2 * E), qkv.cols(2 * E, 3 * E), B, heads, L, L, causal=True)
+            o = self.linear(o, p + ".attn.out_proj.weight", p + ".attn.out_proj.bias")
+            x = self.residual_add(x, o, 0.0)
+            h, _ = self.layernorm(x, p + ".ln_2")
+            m = self.linear(h, p + ".mlp.c_fc.weight", p + ".mlp.c_fc.bias")
+            a = self.quickgelu(m)
+            o = self.linear(a, p + ".mlp.c_proj.weight", p + ".mlp.c_proj.bias")
+            x = self.residual_add(x, o, 0.0)
+        wfeat, _ = self.layernorm(x, b + ".ln_final")
+        sin = self.new(B, E)
+        call("cris_eot_gather", self.word.data_ptr(), wfeat.ptr, 0, wfeat.ld, sin.ptr, sin.ld, B, L, E)
+
+        def bwd_eot():
+            g = self.grad_of(sin)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(wfeat)
+            if not acc:
+                slot.buf.zero_()
+            call("cris_eot_scatter", self.word.data_ptr(), g.ptr, 0, g.ld, slot.ptr, int(slot.fp32), slot.ld, B, L, E)
+
+        if self.training:
+            self.on_backward(bwd_eot)
+        state = self.linear(sin, b + ".text_projection", None, transposed_weight=True)
+        self.tap("word", wfeat)
+        self.tap("state", state)
+        return wfeat, state
+
+    def quickgelu(self, m: Mat) -> Mat:
+        a = self.new(m.rows, m.C, False, None, ld=m.ld)
+        self.ew(3, m, None, a)
+
+        def bwd():
+            g = self.grad_of(a)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(m)
+            assert not acc
+            self.ew(4, m, g, slot)
+
+        if self.training:
+            self.on_backward(bwd)
+        return a
+
+    # ---- FPN neck: model/layers.py:282-309 --------------------------------------------------------------------
+    def fpn(self, c3: Mat, c4: Mat, c5: Mat, state: Mat) -> Mat:
+        B = state.rows
+        n = "neck"
+        zs, part, nt = self.linear(state, n + ".txt_proj.0.weight", None, stats=True)
+        if not self.training:
+            part = None
+        s = self.bn_forward(zs, n + ".txt_proj.1", True, partials=part if self.training else None, n_tiles=nt)
+        f5a = self.conv_bn(c5, n + ".f1_v_proj.0.weight", n + ".f1_v_proj.1", 1)
+        N5, H5, W5 = f5a.geom
+        g = self.new(f5a.rows, f5a.C, False, f5a.geom)
+        rpi = (H5 + 2) * (W5 + 2)
+        call("cris_mul_bcast", f5a.ptr, f5a.ld, s.ptr, s.ld, g.ptr, g.ld, f5a.rows, rpi, f5a.C)
+
+        def bwd_gate():
+            dg = self.grad_of(g)
+            if dg is None:
+                return
+            slot, acc = self.grad_slot(f5a)
+            assert not acc
+            call("cris_mul_bcast", dg.ptr, dg.ld, s.ptr, s.ld, slot.ptr, slot.ld, f5a.rows, rpi, f5a.C)
+            ds = self.f32(B * f5a.C)
+            call("cris_mul_bcast_bwd_s", dg.ptr, dg.ld, f5a.ptr, f5a.ld, ds.data_ptr(), B, rpi, f5a.C)
+            dsm = Mat(ds, B, f5a.C, fp32=True)
+            self.accumulate_into(dsm, s)
+
+        if self.training:
+            self.on_backward(bwd_gate)
+        f5 = self.bn_forward(g, n + ".norm_layer.0", True)
+        fo2, fo1 = f5.C, self.P[n + ".f2_v_proj.0.weight"].shape[0]
+        fo0 = self.P[n + ".f3_v_proj.0.weight"].shape[0]
+        N4, H4, W4 = c4.geom
+        cat2 = self.padded(N4, H4, W4, fo1 + fo2)
+        self.conv_bn(c4, n + ".f2_v_proj.0.weight", n + ".f2_v_proj.1", 3, out=cat2.cols(0, fo1))
+        self.upsample(f5, out=cat2.cols(fo1, fo1 + fo2))
+        cat3 = self.padded(N4, H4, W4, fo0 + fo1)
+        f4 = self.conv_bn(cat2, n + ".f2_cat.0.weight", n + ".f2_cat.1", 1, out=cat3.cols(fo0, fo0 + fo1))
+        f3a = self.conv_bn(c3, n + ".f3_v_proj.0.weight", n + ".f3_v_proj.1", 3)
+        self.avgpool(f3a, out=cat3.cols(0, fo0))
+        f3 = self.conv_bn(cat3, n + ".f3_cat.0.weight", n + ".f3_cat.1", 1)
+        cat4 = self.padded(N4, H4, W4, 3 * fo1)
+        fq5 = self.conv_bn(f5, n + ".f4_proj5.0.weight", n + ".f4_proj5.1", 3)
+        self.conv_bn(f4, n + ".f4_proj4.0.weight", n + ".f4_proj4.1", 3, out=cat4.cols(fo1, 2 * fo1))
+        self.conv_bn(f3, n + ".f4_proj3.0.weight", n + ".f4_proj3.1", 3, out=cat4.cols(0, fo1))
+        self.upsample(fq5, out=cat4.cols(2 * fo1, 3 * fo1))
+        # CoordConv input: [fq | x | y | zero pad] (model/layers.py:30-39)
+        cpad = _r8(fo1 + 2)
+        cbuf = self.padded(N4, H4, W4, cpad)
+        call("cris_coord_fill", cbuf.ptr, cbuf.ld, fo1, N4, H4, W4)
+        self.conv_bn(cat4, n + ".aggr.0.weight", n + ".aggr.1", 1, out=cbuf.cols(0, fo1))
+        cin_view = cbuf.cols(0, fo1 + 2)
+        cin_view.need_grad = True
+        fq = self.conv_bn(cin_view, n + ".coordconv.0.conv1.0.weight", n + ".coordconv.0.conv1.1", 3, cin=fo1 + 2)
+        fq = self.conv_bn(fq, n + ".coordconv.1.0.weight", n + ".coordconv.1.1", 3)
+        self.tap("fq", fq)
+        return fq
+
+    # ---- vision-language decoder: model/layers.py:154-250 ---------------------------------------------------------
+    def decoder(self, fq: Mat, wfeat: Mat) -> Mat:
+        B, H, W = fq.geom
+        C = fq.C
+        T = H * W
+        L = self.word.shape[1]
+        heads = self.model.num_head
+        vpos = self.e.const(("pos2d", C, H, W), lambda: _pos2d(C, H, W), self.dev)
+        tpos = self.e.const(("pos1d", C, L, B), lambda: _pos1d(C, L).repeat(B, 1), self.dev)
+        vis = self.new(B * T, C, True)
+        call("cris_padded_to_tokens", fq.ptr, fq.ld, None, 0, vis.ptr, 1, vis.ld, B, H, W, C)
+
+        def bwd_vis():
+            g = self.grad_of(vis)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(fq)
+            assert not acc
+            call("cris_tokens_to_padded", g.ptr, 1, g.ld, slot.ptr, slot.ld, B, H, W, C)
+
+        if self.training:
+            self.on_backward(bwd_vis)
+        # key input of the cross attention: txt + txt_pos (same for every layer)
+        tk = self.new(B * L, C)
+        tposm = Mat(tpos, B * L, C, fp32=True)
+        self.ew(0, wfeat, tposm, tk)
+
+        def bwd_tk():
+            g = self.grad_of(tk)
+            if g is not None:
+                self.accumulate_into(g, wfeat)
+
+        if self.training:
+            self.on_backward(bwd_tk)
+        p_drop = self.p_drop
+        for i in range(len(self.model.decoder.layers)):
+            p = f"decoder.layers.{i}"
+            # self attention: q = k = LN(vis) + pos, v = LN(vis)
+            v2, v2p = self.layernorm(vis, p + ".norm1", add=vpos, want_y=True, want_y2=True)
+            qk = self.linear(v2p, p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias", w_rows=(0, 2 * C))
+            vv = self.linear(v2, p + ".self_attn.in_proj_weight", p + ".self_attn.in_proj_bias", w_rows=(2 * C, 3 * C))
+            a = self.attention(qk.cols(0, C), qk.cols(C, 2 * C), vv, B, heads, T, T, p_drop=p_drop)
+            a = self.linear(a, p + ".self_attn.out_proj.weight", p + ".self_attn.out_proj.bias")
+            a, _ = self.layernorm(a, p + ".self_attn_norm")
+            vis = self.residual_add(vis, a, p_drop)
+            # cross attention: q = LN(vis) + pos, k = txt + txt_pos, v = txt; padded tokens masked
+            _, v2p = self.layernorm(vis, p + ".norm2", add=vpos, want_y=False, want_y2=True)
+            q = self.linear(v2p, p + ".multihead_attn.in_proj_weight", p + ".multihead_attn.in_proj_bias", w_rows=(0, C))
+            k = self.linear(tk, p + ".multihead_attn.in_proj_weight", p + ".multihead_attn.in_proj_bias",
+                            w_rows=(C, 2 * C))
+            vv = self.linear(wfeat, p + ".multihead_attn.in_proj_weight", p + ".multihead_attn.in_proj_bias",
+                             w_rows=(2 * C, 3 * C))
+            a = self.attention(q, k, vv, B, heads, T, L, key_pad=True, p_drop=p_drop)
+            a = self.linear(a, p + ".multihead_attn.out_proj.weight", p + ".multihead_attn.out_proj.bias")
+            a, _ = self.layernorm(a, p + ".cross_attn_norm")
+            vis = self.residual_add(vis, a, p_drop)
+            # FFN: Linear -> ReLU -> Dropout -> LayerNorm(ffn) -> Linear
+            v2, _ = self.layernorm(vis, p + ".norm3")
+            h = self.linear(v2, p + ".ffn.0.weight", p + ".ffn.0.bias", act=ACT_RELU)
+            if p_drop > 0:
+                h = self.dropout(h, p_drop)
+            h, _ = self.layernorm(h, p + ".ffn.3")
+            h = self.linear(h, p + ".ffn.4.weight", p + ".ffn.4.bias")
+            vis = self.residual_add(vis, h, p_drop)
+            self.tap(f"dec{i}", vis)
+        out, _ = self.layernorm(vis, "decoder.norm")
+        fo = self.padded(B, H, W, C)
+        call("cris_tokens_to_padded", out.ptr, 0, out.ld, fo.ptr, fo.ld, B, H, W, C)
+
+        def bwd_fo():
+            g = self.grad_of(fo)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(out)
+            assert not acc
+            call("cris_padded_to_tokens", g.ptr, g.ld, None, 0, slot.ptr, 0, slot.ld, B, H, W, C)
+
+        if self.training:
+            self.on_backward(bwd_fo)
+        self.tap("dec_out", fo)
+        return fo
+
+    def dropout(self, x: Mat, p: float) -> Mat:
+        y = self.new(x.rows, x.C, False, None, ld=x.ld)
+        sd = self.seed()
+        self.ew(2, x, None, y, p, sd)
+
+        def bwd():
+            g = self.grad_of(y)
+            if g is None:
+                return
+            slot, acc = self.grad_slot(x)
+            assert not acc
+            self.ew(2, g, None, slot, p, sd)
+
+        if self.training:
+            self.on_backward(bwd)
+        return y
+
+    # ---- projector + loss: model/layers.py:63-84, model/segmenter.py:52-62 ---------------------------------------
+    def projector_and_loss(self, fq: Mat, state: Mat):
+        B, H, W = fq.geom
+        x = self.upsample(fq)
+        x = self.conv_bn(x, "proj.vis.1.0.weight", "proj.vis.1.1", 3)
+        x = self.upsample(x)
+        x = self.conv_bn(x, "proj.vis.3.0.weight", "proj.vis.3.1", 3)
+        xf, _, _ = self.conv(x, "proj.vis.4.weight", 1, stats=False, bias_name="proj.vis.4.bias")
+        self.tap("proj_feat", xf)
+        C = xf.C
+        Ho, Wo = xf.geom[1], xf.geom[2]
+        t = self.linear(state, "proj.txt.weight", "proj.txt.bias", out_fp32=True)
+        pred = torch.empty(B, 1, Ho, Wo, dtype=torch.float32, device=self.dev)
+        mask_out = torch.empty(B, 1, Ho, Wo, dtype=torch.float32, device=self.dev) if self.mask is not None else None
+        loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        Hm, Wm = (self.mask.shape[-2], self.mask.shape[-1]) if self.mask is not None else (0, 0)
+        call("cris_dynconv_bce_fwd", xf.ptr, xf.ld, t.ptr, t.ld, self.mask.data_ptr() if self.mask is not None else None,
+             Hm, Wm, pred.data_ptr(), mask_out.data_ptr() if mask_out is not None else None, loss.data_ptr(), B, Ho, Wo,
+             C)
+        self.pred, self.mask_out, self.loss = pred, mask_out, loss
+        self._head = (xf, t, B, Ho, Wo, C)
+
+    # =================================================================================================
+    def backward(self, dloss: torch.Tensor, names: List[str]):
+        xf, t, B, Ho, Wo, C = self._head
+        g = dloss.detach().float().reshape(1).contiguous()
+        dl = self.f32(B * Ho * Wo)
+        dxf, _ = self.grad_slot(xf)
+        dt, _ = self.grad_slot(t)
+        dt.buf.zero_()
+        call("cris_dynconv_bce_bwd", xf.ptr, xf.ld, t.ptr, t.ld, self.pred.data_ptr(), self.mask_out.data_ptr(),
+             g.data_ptr(), dl.data_ptr(), dxf.ptr, dxf.ld, dt.ptr, dt.ld, B, Ho, Wo, C)
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        out = []
+        for k in names:
+            out.append(self.pgrad.get(k))
+        missing = [k for k, gk in zip(names, out) if gk is None]
+        if missing:
+            raise RuntimeError(f"cris.pytorch_b200 backward produced no gradient for {missing[:5]}")
+        return out

@@ -164,7 +164,7 @@ int cris_stem_conv1_wgrad(const float* img, const void* dz, int64_t lddz, float*
 /* ---- token ops (softmax/dropout inside MHA clip.py:119-139,255-260, layers.py:235,240-243; nn.Embedding
  *      clip.py:440-443; EOT gather clip.py:451-452; residual dropout layers.py:237,245,249; QuickGELU clip.py:234-236) */
 int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
-                     int heads, const uint8_t* kpm, int causal, float p_drop, uint64_t seed, void* stream);
+                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, void* stream);
 int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
                      uint64_t seed, void* stream);
 int cris_embed_fwd(const int64_t* word, const float* table, const float* pos, float* x, int B, int L, int C,
