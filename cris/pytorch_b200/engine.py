@@ -264,7 +264,7 @@ class Run:
         root = m.root if m.root is not None else m
         if root.gbuf is None:
             whole = m.root is None
-            g = self.new(root.rows, root.C, root.fp32, root.geom, zero=not whole, ld=None)
+            g = self.new(root.rows, root.C, root.fp32, root.geom, zero=not whole, ld=root.ld)
             root.gbuf = g
             root.gwritten = True
             if whole:

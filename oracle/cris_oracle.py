@@ -32,12 +32,30 @@ LN_EPS = 1e-5
 class OracleState:
     """Carries mode flags and collects updated BatchNorm running statistics."""
 
-    def __init__(self, sd: SD, training: bool, dropout_p: float = 0.0, taps: Optional[dict] = None):
+    def __init__(self, sd: SD, training: bool, dropout_p: float = 0.0, taps: Optional[dict] = None,
+                 storage: str = "fp32"):
         self.sd = sd
         self.training = training
         self.dropout_p = dropout_p
         self.new_running: Dict[str, Tensor] = {}
         self.taps = taps  # optional dict collecting named intermediates
+        # storage = "fp32": the reference algorithm in full precision (what the golden fixtures pin).
+        # storage = "bf16": the SAME algorithm with every tensor that cris.pytorch_b200 keeps in bf16
+        # (GEMM operands/outputs, activations; DESIGN.md §3) rounded to bf16 where it is stored — the
+        # same-precision comparison that autocast gives the reference (engine/engine.py:48).  Rounding uses
+        # a straight-through gradient so autograd still yields the reference gradients at those activations.
+        assert storage in ("fp32", "bf16")
+        self.storage = storage
+
+    def q(self, x: Tensor) -> Tensor:
+        """activation storage rounding"""
+        if self.storage == "fp32":
+            return x
+        return x + (x.to(torch.bfloat16).float() - x).detach()
+
+    def w(self, name: str) -> Tensor:
+        """GEMM weight operand (conv / linear / in_proj / text_projection are bf16 tensor-core operands)"""
+        return self.q(self.sd[name])
 
     def tap(self, name: str, t: Tensor) -> Tensor:
         if self.taps is not None:
@@ -102,14 +120,17 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, add_mask: Optional[Te
     kh = k.view(B, Lk, heads, hd).transpose(1, 2)
     vh = v.view(B, Lk, heads, hd).transpose(1, 2)
     s = (qh @ kh.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
+    if st is not None:
+        s = st.q(s)
     if add_mask is not None:
         s = s + add_mask
     if key_padding is not None:
         s = s.masked_fill(key_padding[:, None, None, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
     if st is not None:
-        p = dropout(st, p)
-    return (p @ vh).transpose(1, 2).reshape(B, Lq, E)
+        p = st.q(dropout(st, st.q(p)))
+    o = (p @ vh).transpose(1, 2).reshape(B, Lq, E)
+    return st.q(o) if st is not None else o
 
 
 # --------------------------------------------------------------------------------------------
@@ -118,18 +139,18 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, add_mask: Optional[Te
 def bottleneck(st: OracleState, x: Tensor, p: str, stride: int) -> Tensor:
     """model/clip.py:44-57: 1x1 -> BN -> ReLU -> 3x3 (stride 1) -> BN -> ReLU -> AvgPool(stride)
     -> 1x1 -> BN, identity through [AvgPool(stride) -> 1x1 -> BN] when shapes change, add, ReLU."""
-    sd = st.sd
-    out = F.relu(batch_norm(st, F.conv2d(x, sd[p + ".conv1.weight"]), p + ".bn1"))
-    out = F.relu(batch_norm(st, F.conv2d(out, sd[p + ".conv2.weight"], padding=1), p + ".bn2"))
+    sd, q = st.sd, st.q
+    out = q(F.relu(batch_norm(st, q(F.conv2d(x, st.w(p + ".conv1.weight"))), p + ".bn1")))
+    out = q(F.relu(batch_norm(st, q(F.conv2d(out, st.w(p + ".conv2.weight"), padding=1)), p + ".bn2")))
     if stride > 1:
-        out = F.avg_pool2d(out, stride)
-    out = batch_norm(st, F.conv2d(out, sd[p + ".conv3.weight"]), p + ".bn3")
+        out = q(F.avg_pool2d(out, stride))
+    out = batch_norm(st, q(F.conv2d(out, st.w(p + ".conv3.weight"))), p + ".bn3")
     if (p + ".downsample.0.weight") in sd:
-        idn = F.avg_pool2d(x, stride) if stride > 1 else x
-        idn = batch_norm(st, F.conv2d(idn, sd[p + ".downsample.0.weight"]), p + ".downsample.1")
+        idn = q(F.avg_pool2d(x, stride)) if stride > 1 else x
+        idn = q(batch_norm(st, q(F.conv2d(idn, st.w(p + ".downsample.0.weight"))), p + ".downsample.1"))
     else:
         idn = x
-    return F.relu(out + idn)
+    return q(F.relu(out + idn))
 
 
 def resized_pos_embed(pos: Tensor, spacial: int, hw) -> Tensor:
@@ -146,26 +167,29 @@ def attention_pool(st: OracleState, x: Tensor, p: str, heads: int) -> Tensor:
     (separate q/k/v weights, no dropout), c_proj, + residual, ReLU."""
     sd = st.sd
     B, C, H, W = x.shape
-    res = batch_norm(st, F.conv2d(x, sd[p + ".connect.0.weight"]), p + ".connect.1")
+    rq = st.q
+    res = batch_norm(st, rq(F.conv2d(x, st.w(p + ".connect.0.weight"))), p + ".connect.1")
     spacial = int(round(math.sqrt(sd[p + ".positional_embedding"].shape[0] - 1)))
-    tok = x.flatten(2).transpose(1, 2) + resized_pos_embed(sd[p + ".positional_embedding"], spacial, (H, W))
-    q = F.linear(tok, sd[p + ".q_proj.weight"], sd[p + ".q_proj.bias"])
-    k = F.linear(tok, sd[p + ".k_proj.weight"], sd[p + ".k_proj.bias"])
-    v = F.linear(tok, sd[p + ".v_proj.weight"], sd[p + ".v_proj.bias"])
-    o = attention(q, k, v, heads)
-    o = F.linear(o, sd[p + ".c_proj.weight"], sd[p + ".c_proj.bias"])
+    tok = rq(x.flatten(2).transpose(1, 2) + resized_pos_embed(sd[p + ".positional_embedding"], spacial, (H, W)))
+    q = rq(F.linear(tok, st.w(p + ".q_proj.weight"), sd[p + ".q_proj.bias"]))
+    k = rq(F.linear(tok, st.w(p + ".k_proj.weight"), sd[p + ".k_proj.bias"]))
+    v = rq(F.linear(tok, st.w(p + ".v_proj.weight"), sd[p + ".v_proj.bias"]))
+    o = attention(q, k, v, heads, st=st if st.storage != "fp32" else None)
+    o = rq(F.linear(o, st.w(p + ".c_proj.weight"), sd[p + ".c_proj.bias"]))
     o = o.transpose(1, 2).reshape(B, -1, H, W)
-    return F.relu(o + res)
+    return rq(F.relu(o + res))
 
 
 def encode_image(st: OracleState, img: Tensor):
     """model/clip.py:207-223 (+ :436-437): 3-conv stem, avgpool, layer1..4, attnpool -> (C3,C4,C5)."""
     sd = st.sd
     v = "backbone.visual"
-    x = F.relu(batch_norm(st, F.conv2d(img, sd[v + ".conv1.weight"], stride=2, padding=1), v + ".bn1"))
-    x = F.relu(batch_norm(st, F.conv2d(x, sd[v + ".conv2.weight"], padding=1), v + ".bn2"))
-    x = F.relu(batch_norm(st, F.conv2d(x, sd[v + ".conv3.weight"], padding=1), v + ".bn3"))
-    x = F.avg_pool2d(x, 2)
+    q = st.q
+    # stem conv1 runs on the fp32 image with fp32 weights (its 27-tap kernel is not a tensor-core GEMM)
+    x = q(F.relu(batch_norm(st, q(F.conv2d(img, sd[v + ".conv1.weight"], stride=2, padding=1)), v + ".bn1")))
+    x = q(F.relu(batch_norm(st, q(F.conv2d(x, st.w(v + ".conv2.weight"), padding=1)), v + ".bn2")))
+    x = q(F.relu(batch_norm(st, q(F.conv2d(x, st.w(v + ".conv3.weight"), padding=1)), v + ".bn3")))
+    x = q(F.avg_pool2d(x, 2))
     st.tap("stem", x)
     feats = []
     for li in (1, 2, 3, 4):
@@ -200,19 +224,20 @@ def encode_text(st: OracleState, word: Tensor):
     i = 0
     while f"{b}.transformer.resblocks.{i}.ln_1.weight" in sd:
         p = f"{b}.transformer.resblocks.{i}"
-        h = layer_norm(st, x, p + ".ln_1")
-        qkv = F.linear(h, sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"])
+        rq = st.q
+        h = rq(layer_norm(st, x, p + ".ln_1"))
+        qkv = rq(F.linear(h, st.w(p + ".attn.in_proj_weight"), sd[p + ".attn.in_proj_bias"]))
         q, k, v = qkv.split(width, dim=-1)
-        a = attention(q, k, v, heads, add_mask=causal)
-        x = x + F.linear(a, sd[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"])
-        h = layer_norm(st, x, p + ".ln_2")
-        h = F.linear(h, sd[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"])
-        h = h * torch.sigmoid(1.702 * h)
-        x = x + F.linear(h, sd[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"])
+        a = attention(q, k, v, heads, add_mask=causal, st=st if st.storage != "fp32" else None)
+        x = x + rq(F.linear(a, st.w(p + ".attn.out_proj.weight"), sd[p + ".attn.out_proj.bias"]))
+        h = rq(layer_norm(st, x, p + ".ln_2"))
+        h = rq(F.linear(h, st.w(p + ".mlp.c_fc.weight"), sd[p + ".mlp.c_fc.bias"]))
+        h = rq(h * torch.sigmoid(1.702 * h))
+        x = x + rq(F.linear(h, st.w(p + ".mlp.c_proj.weight"), sd[p + ".mlp.c_proj.bias"]))
         i += 1
-    x = layer_norm(st, x, b + ".ln_final")
+    x = st.q(layer_norm(st, x, b + ".ln_final"))
     eot = word.argmax(dim=-1)
-    state = x[torch.arange(B), eot] @ sd[b + ".text_projection"]
+    state = st.q(x[torch.arange(B), eot] @ st.w(b + ".text_projection"))
     st.tap("word", x)
     st.tap("state", state)
     return x, state
@@ -223,27 +248,29 @@ def encode_text(st: OracleState, word: Tensor):
 # --------------------------------------------------------------------------------------------
 def conv_bn_relu(st: OracleState, x: Tensor, p: str, pad: int) -> Tensor:
     """model/layers.py:8-11 conv_layer: Conv2d(no bias) + BN + ReLU."""
-    return F.relu(batch_norm(st, F.conv2d(x, st.sd[p + ".0.weight"], padding=pad), p + ".1"))
+    return st.q(F.relu(batch_norm(st, st.q(F.conv2d(x, st.w(p + ".0.weight"), padding=pad)), p + ".1")))
 
 
-def up2(x: Tensor) -> Tensor:
+def up2(x: Tensor, st: Optional[OracleState] = None) -> Tensor:
     """bilinear x2, align_corners=False (model/layers.py:54,56,293,304)."""
-    return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    return st.q(y) if st is not None else y
 
 
 def fpn(st: OracleState, c3: Tensor, c4: Tensor, c5: Tensor, state: Tensor) -> Tensor:
     """model/layers.py:282-309."""
     sd = st.sd
-    s = F.linear(state, sd["neck.txt_proj.0.weight"])
-    s = F.relu(batch_norm(st, s, "neck.txt_proj.1"))[:, :, None, None]
+    q = st.q
+    s = q(F.linear(state, st.w("neck.txt_proj.0.weight")))
+    s = q(F.relu(batch_norm(st, s, "neck.txt_proj.1")))[:, :, None, None]
     f5 = conv_bn_relu(st, c5, "neck.f1_v_proj", 0)
-    f5 = F.relu(batch_norm(st, f5 * s, "neck.norm_layer.0"))
+    f5 = q(F.relu(batch_norm(st, q(f5 * s), "neck.norm_layer.0")))
     f4 = conv_bn_relu(st, c4, "neck.f2_v_proj", 1)
-    f4 = conv_bn_relu(st, torch.cat([f4, up2(f5)], 1), "neck.f2_cat", 0)
+    f4 = conv_bn_relu(st, torch.cat([f4, up2(f5, st)], 1), "neck.f2_cat", 0)
     f3 = conv_bn_relu(st, c3, "neck.f3_v_proj", 1)
-    f3 = F.avg_pool2d(f3, 2, 2)
+    f3 = q(F.avg_pool2d(f3, 2, 2))
     f3 = conv_bn_relu(st, torch.cat([f3, f4], 1), "neck.f3_cat", 0)
-    fq5 = up2(conv_bn_relu(st, f5, "neck.f4_proj5", 1))
+    fq5 = up2(conv_bn_relu(st, f5, "neck.f4_proj5", 1), st)
     fq4 = conv_bn_relu(st, f4, "neck.f4_proj4", 1)
     fq3 = conv_bn_relu(st, f3, "neck.f4_proj3", 1)
     fq = conv_bn_relu(st, torch.cat([fq3, fq4, fq5], 1), "neck.aggr", 0)
@@ -251,7 +278,7 @@ def fpn(st: OracleState, c3: Tensor, c4: Tensor, c5: Tensor, state: Tensor) -> T
     B, _, H, W = fq.shape
     ys = torch.linspace(-1, 1, H).view(1, 1, H, 1).expand(B, 1, H, W)
     xs = torch.linspace(-1, 1, W).view(1, 1, 1, W).expand(B, 1, H, W)
-    fq = conv_bn_relu(st, torch.cat([fq, xs, ys], 1), "neck.coordconv.0.conv1", 1)
+    fq = conv_bn_relu(st, torch.cat([fq, q(xs), q(ys)], 1), "neck.coordconv.0.conv1", 1)
     fq = conv_bn_relu(st, fq, "neck.coordconv.1", 1)
     return st.tap("fq", fq)
 
@@ -283,13 +310,13 @@ def sine_pos_2d(d: int, H: int, W: int) -> Tensor:
     return pe.reshape(H * W, d)
 
 
-def mha_proj(sd: SD, p: str, q_in: Tensor, k_in: Tensor, v_in: Tensor):
+def mha_proj(st: OracleState, p: str, q_in: Tensor, k_in: Tensor, v_in: Tensor):
     """Packed in_proj of nn.MultiheadAttention applied to three different inputs."""
-    w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    w, b = st.w(p + ".in_proj_weight"), st.sd[p + ".in_proj_bias"]
     E = w.shape[1]
-    q = F.linear(q_in, w[:E], b[:E])
-    k = F.linear(k_in, w[E:2 * E], b[E:2 * E])
-    v = F.linear(v_in, w[2 * E:], b[2 * E:])
+    q = st.q(F.linear(q_in, w[:E], b[:E]))
+    k = st.q(F.linear(k_in, w[E:2 * E], b[E:2 * E]))
+    v = st.q(F.linear(v_in, w[2 * E:], b[2 * E:]))
     return q, k, v
 
 
@@ -300,28 +327,31 @@ def decoder(st: OracleState, fq: Tensor, word: Tensor, pad_mask: Tensor, heads: 
     L = word.shape[1]
     vpos = sine_pos_2d(C, H, W)
     tpos = sine_pos_1d(word.shape[2], L)
+    rq = st.q
     vis = fq.flatten(2).transpose(1, 2)  # [B, HW, C]
+    tk = rq(word + tpos)
     i = 0
     while f"decoder.layers.{i}.norm1.weight" in sd:
         p = f"decoder.layers.{i}"
-        v2 = layer_norm(st, vis, p + ".norm1")
-        q, k, v = mha_proj(sd, p + ".self_attn", v2 + vpos, v2 + vpos, v2)
+        ln = layer_norm(st, vis, p + ".norm1")
+        v2, v2p = rq(ln), rq(ln + vpos)
+        q, k, v = mha_proj(st, p + ".self_attn", v2p, v2p, v2)
         a = attention(q, k, v, heads, st=st)
-        a = F.linear(a, sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"])
-        vis = vis + dropout(st, layer_norm(st, a, p + ".self_attn_norm"))
-        v2 = layer_norm(st, vis, p + ".norm2")
-        q, k, v = mha_proj(sd, p + ".multihead_attn", v2 + vpos, word + tpos, word)
+        a = rq(F.linear(a, st.w(p + ".self_attn.out_proj.weight"), sd[p + ".self_attn.out_proj.bias"]))
+        vis = vis + dropout(st, rq(layer_norm(st, a, p + ".self_attn_norm")))
+        v2p = rq(layer_norm(st, vis, p + ".norm2") + vpos)
+        q, k, v = mha_proj(st, p + ".multihead_attn", v2p, tk, word)
         a = attention(q, k, v, heads, key_padding=pad_mask, st=st)
-        a = F.linear(a, sd[p + ".multihead_attn.out_proj.weight"], sd[p + ".multihead_attn.out_proj.bias"])
-        vis = vis + dropout(st, layer_norm(st, a, p + ".cross_attn_norm"))
-        v2 = layer_norm(st, vis, p + ".norm3")
-        h = F.relu(F.linear(v2, sd[p + ".ffn.0.weight"], sd[p + ".ffn.0.bias"]))
-        h = layer_norm(st, dropout(st, h), p + ".ffn.3")
-        h = F.linear(h, sd[p + ".ffn.4.weight"], sd[p + ".ffn.4.bias"])
+        a = rq(F.linear(a, st.w(p + ".multihead_attn.out_proj.weight"), sd[p + ".multihead_attn.out_proj.bias"]))
+        vis = vis + dropout(st, rq(layer_norm(st, a, p + ".cross_attn_norm")))
+        v2 = rq(layer_norm(st, vis, p + ".norm3"))
+        h = rq(F.relu(F.linear(v2, st.w(p + ".ffn.0.weight"), sd[p + ".ffn.0.bias"])))
+        h = rq(layer_norm(st, dropout(st, h), p + ".ffn.3"))
+        h = rq(F.linear(h, st.w(p + ".ffn.4.weight"), sd[p + ".ffn.4.bias"]))
         vis = vis + dropout(st, h)
         st.tap(f"dec{i}", vis)
         i += 1
-    vis = layer_norm(st, vis, "decoder.norm")
+    vis = rq(layer_norm(st, vis, "decoder.norm"))
     return vis.transpose(1, 2).reshape(B, C, H, W)
 
 
@@ -332,12 +362,12 @@ def projector(st: OracleState, fq: Tensor, state: Tensor) -> Tensor:
     """model/layers.py:63-84: up x2, conv3x3+BN+ReLU, up x2, conv3x3+BN+ReLU, conv1x1(+bias); the
     text Linear yields per-sample 3x3 kernels [B,C,3,3] and a bias [B]; per-sample correlation."""
     sd = st.sd
-    x = conv_bn_relu(st, up2(fq), "proj.vis.1", 1)
-    x = conv_bn_relu(st, up2(x), "proj.vis.3", 1)
-    x = F.conv2d(x, sd["proj.vis.4.weight"], sd["proj.vis.4.bias"])
+    x = conv_bn_relu(st, up2(fq, st), "proj.vis.1", 1)
+    x = conv_bn_relu(st, up2(x, st), "proj.vis.3", 1)
+    x = st.q(F.conv2d(x, st.w("proj.vis.4.weight"), sd["proj.vis.4.bias"]))
     st.tap("proj_feat", x)
     B, C, H, W = x.shape
-    t = F.linear(state, sd["proj.txt.weight"], sd["proj.txt.bias"])
+    t = F.linear(state, st.w("proj.txt.weight"), sd["proj.txt.bias"])  # kept in fp32 by the engine too
     kern, bias = t[:, :-1].reshape(B, C, 3, 3), t[:, -1]
     patches = F.unfold(x, 3, padding=1).view(B, C * 9, H * W)
     out = torch.einsum("bkp,bk->bp", patches, kern.reshape(B, C * 9)) + bias[:, None]
@@ -345,9 +375,10 @@ def projector(st: OracleState, fq: Tensor, state: Tensor) -> Tensor:
 
 
 def cris_forward(sd: SD, img: Tensor, word: Tensor, mask: Optional[Tensor] = None, *, training: bool = False,
-                 num_head: int = 8, dropout_p: float = 0.0, taps: Optional[dict] = None):
-    """model/segmenter.py:29-62.  Returns dict(pred, mask, loss, new_running)."""
-    st = OracleState(sd, training, dropout_p, taps)
+                 num_head: int = 8, dropout_p: float = 0.0, taps: Optional[dict] = None, storage: str = "fp32"):
+    """model/segmenter.py:29-62.  Returns dict(pred, mask, loss, new_running).
+    storage="bf16" = same algorithm with the engine's bf16 storage points emulated (see OracleState)."""
+    st = OracleState(sd, training, dropout_p, taps, storage)
     pad_mask = word == 0
     c3, c4, c5 = encode_image(st, img)
     wfeat, state = encode_text(st, word)

@@ -75,7 +75,13 @@ def _ln(sd, g: _Gen, name: str, c: int):
 def clip_state_dict(arch: str = "r50", seed: int = 0) -> Dict[str, torch.Tensor]:
     """A CLIP-ResNet-shaped state_dict with the key set OpenAI's TorchScript files carry PLUS the
     CRIS-added `visual.attnpool.connect.*` (model/clip.py:76-78); names per SURVEY.md Appendix B
-    without the `backbone.` prefix."""
+    without the `backbone.` prefix.
+
+    Conditioning: the last BatchNorm of every bottleneck gets a small gamma (0.05-0.15), as in trained /
+    zero-init-residual ResNets (CLIP's own init zeroes it, model/clip.py:402-408).  With O(1) gammas a
+    random-weight ResNet in batch-statistics mode is chaotic: bf16 storage noise grows ~2x per stage
+    (12 % at layer4), for the reference under autocast as much as for this build, which would make
+    any fp32-vs-bf16 comparison meaningless."""
     a = ARCHS[arch]
     g = _Gen(seed)
     sd: Dict[str, torch.Tensor] = {}
@@ -92,7 +98,7 @@ def clip_state_dict(arch: str = "r50", seed: int = 0) -> Dict[str, torch.Tensor]
             stride = 2 if (li > 1 and bi == 0) else 1
             _conv(sd, g, p + ".conv1.weight", planes, inpl, 1); _bn(sd, g, p + ".bn1", planes)
             _conv(sd, g, p + ".conv2.weight", planes, planes, 3); _bn(sd, g, p + ".bn2", planes)
-            _conv(sd, g, p + ".conv3.weight", planes * 4, planes, 1); _bn(sd, g, p + ".bn3", planes * 4, gamma=(0.2, 0.6))
+            _conv(sd, g, p + ".conv3.weight", planes * 4, planes, 1); _bn(sd, g, p + ".bn3", planes * 4, gamma=(0.05, 0.15))
             if stride > 1 or inpl != planes * 4:
                 _conv(sd, g, p + ".downsample.0.weight", planes * 4, inpl, 1, gain=1.0)
                 _bn(sd, g, p + ".downsample.1", planes * 4)
@@ -168,7 +174,9 @@ def head_state_dict(cfg, seed: int = 1) -> Dict[str, torch.Tensor]:
     # small dynamic kernels keep the logits O(1) and centred near the 0.35 threshold
     sd["proj.txt.weight"] = g.normal(c * 9 + 1, cfg.word_dim, std=0.35 / math.sqrt(cfg.word_dim * c * 9))
     sd["proj.txt.bias"] = g.normal(c * 9 + 1, std=0.002)
-    sd["proj.txt.bias"][-1] = -0.619
+    # centre the eval logits on the mask threshold sigmoid(l) > 0.35 <=> l > -0.619 so that thresholded-mask /
+    # IoU comparisons are not vacuous; offsets measured once per arch with these seeds
+    sd["proj.txt.bias"][-1] = {512: 0.10, 128: -0.52}.get(cfg.vis_dim, 0.10)
     return sd
 
 

@@ -1,0 +1,385 @@
+"""GPU: per-op parity of the engine's building blocks (forward AND backward) against plain PyTorch fp32
+math on the same bf16-rounded inputs.  Tolerances are relative L2 errors sized for bf16 storage."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_run(params=None, buffers=None, training=True, p_drop=0.0):
+    from cris.pytorch_b200 import engine as E
+
+    class _Eng:
+        def __init__(self):
+            self.packed = E.PackedWeights()
+            self.consts = {}
+            self.debug_taps = None
+            self.step = 0
+
+        const = E.Engine.const
+
+    r = object.__new__(E.Run)
+    r.e = _Eng()
+    r.dev = torch.device("cuda")
+    r.training, r.record = training, training
+    r.tape, r.pgrad = [], {}
+    r.P = {k: v.cuda() for k, v in (params or {}).items()}
+    r.Bf = {k: v.cuda() for k, v in (buffers or {}).items()}
+    r.p_drop = p_drop
+    r.seed_base, r.n_seed = 1234567, 0
+    r.world, r.sync_bn = 1, False
+    return r
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def to_padded(run, x_nchw):
+    from cris.pytorch_b200.engine import Mat
+    N, C, H, W = x_nchw.shape
+    buf = torch.zeros(N, H + 2, W + 2, C, dtype=torch.bfloat16, device="cuda")
+    buf[:, 1:-1, 1:-1, :] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return Mat(buf.reshape(-1, C), N * (H + 2) * (W + 2), C, geom=(N, H, W))
+
+
+def to_mat(run, x2d, fp32=False):
+    from cris.pytorch_b200.engine import Mat
+    t = x2d.cuda().to(torch.float32 if fp32 else torch.bfloat16).contiguous()
+    return Mat(t, t.shape[0], t.shape[1], fp32=fp32)
+
+
+def out_t(m):
+    from cris.pytorch_b200.engine import mat_to_torch
+    return mat_to_torch(m).cpu()
+
+
+def set_grad(run, m, g):
+    """seed grad(m) with tensor g (NCHW for image Mats, [rows, C] otherwise)"""
+    slot, _ = run.grad_slot(m)
+    if m.geom is not None:
+        N, H, W = m.geom
+        full = torch.zeros(N, H + 2, W + 2, m.C, device="cuda")
+        full[:, 1:-1, 1:-1, :] = g.cuda().permute(0, 2, 3, 1)
+        g2 = full.reshape(-1, m.C)
+    else:
+        g2 = g.cuda()
+    view = torch.as_strided(slot.buf.reshape(-1), (slot.rows, slot.C), (slot.ld, 1),
+                            (slot.ptr - slot.buf.data_ptr()) // slot.esize)
+    view.copy_(g2.to(view.dtype))
+
+
+def backward(run):
+    for fn in reversed(run.tape):
+        fn()
+    run.tape = []
+    torch.cuda.synchronize()
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _bn_params(g, name, c):
+    return ({name + ".weight": torch.rand(c, generator=g) + 0.5, name + ".bias": torch.randn(c, generator=g) * 0.1},
+            {name + ".running_mean": torch.randn(c, generator=g) * 0.1, name + ".running_var": torch.rand(c, generator=g) + 0.5,
+             name + ".num_batches_tracked": torch.zeros((), dtype=torch.long)})
+
+
+@pytest.mark.parametrize("k,cin,cout,resid,relu", [(1, 64, 128, False, True), (3, 64, 64, False, True),
+                                                   (3, 32, 32, False, True), (1, 128, 256, True, True),
+                                                   (3, 130, 64, False, False), (3, 256, 512, False, True)])
+def test_conv_bn_train(k, cin, cout, resid, relu):
+    g = torch.Generator().manual_seed(k * 100 + cin)
+    N, H, W = 3, 12, 10
+    x = _bf(torch.randn(N, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+    P, Bf = _bn_params(g, "bn", cout)
+    P["conv.weight"] = w
+    res = _bf(torch.randn(N, cout, H, W, generator=g)) if resid else None
+    run = _mk_run(P, Bf)
+    xm = to_padded(run, x)
+    rm = to_padded(run, res) if resid else None
+    y = run.conv_bn(xm, "conv.weight", "bn", k, relu=relu, resid=rm, cin=cin)
+    gy = _bf(torch.randn(N, cout, H, W, generator=g))
+    set_grad(run, y, gy)
+    backward(run)
+    # reference
+    xr = x.clone().requires_grad_(True)
+    wr = _bf(w).requires_grad_(True)
+    gam = P["bn.weight"].clone().requires_grad_(True)
+    bet = P["bn.bias"].clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if resid else None
+    z = F.conv2d(xr, wr, padding=k // 2)
+    o = F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5)
+    if resid:
+        o = o + rr
+    if relu:
+        o = F.relu(o)
+    o.backward(gy)
+    assert rel(out_t(y), o.detach()) < 1.5e-2
+    assert rel(out_t(run.grad_of(xm)), xr.grad) < 3e-2
+    assert rel(run.pgrad["conv.weight"].cpu(), wr.grad) < 3e-2
+    assert rel(run.pgrad["bn.weight"].cpu(), gam.grad) < 5e-2  # relu(resid + bn) masks flip on bf16 ties
+    assert rel(run.pgrad["bn.bias"].cpu(), bet.grad) < 5e-2
+    if resid:
+        assert rel(out_t(run.grad_of(rm)), rr.grad) < 2e-2
+    # running statistics (momentum 0.1, unbiased variance)
+    n = N * H * W
+    zz = F.conv2d(x, _bf(w), padding=k // 2)
+    exp_rm = 0.9 * Bf["bn.running_mean"] + 0.1 * zz.mean((0, 2, 3))
+    exp_rv = 0.9 * Bf["bn.running_var"] + 0.1 * zz.var((0, 2, 3), unbiased=False) * n / (n - 1)
+    assert rel(run.Bf["bn.running_mean"].cpu(), exp_rm) < 1e-2
+    assert rel(run.Bf["bn.running_var"].cpu(), exp_rv) < 1e-2
+
+
+def test_conv_bn_eval_and_bias_conv():
+    g = torch.Generator().manual_seed(5)
+    N, H, W, cin, cout = 2, 9, 11, 64, 64
+    x = _bf(torch.randn(N, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    P, Bf = _bn_params(g, "bn", cout)
+    P["conv.weight"] = w
+    P["c1.weight"] = torch.randn(cout, cin, 1, 1, generator=g) * 0.1
+    P["c1.bias"] = torch.randn(cout, generator=g)
+    run = _mk_run(P, Bf, training=False)
+    y = run.conv_bn(to_padded(run, x), "conv.weight", "bn", 3)
+    ref = F.relu(F.batch_norm(F.conv2d(x, _bf(w), padding=1), Bf["bn.running_mean"], Bf["bn.running_var"],
+                              P["bn.weight"], P["bn.bias"], False, 0.1, 1e-5))
+    assert rel(out_t(y), ref) < 1e-2
+    run = _mk_run(P, Bf, training=True)
+    xm = to_padded(run, x)
+    z, _, _ = run.conv(xm, "c1.weight", 1, stats=False, bias_name="c1.bias")
+    gz = _bf(torch.randn(N, cout, H, W, generator=g))
+    set_grad(run, z, gz)
+    backward(run)
+    xr = x.clone().requires_grad_(True)
+    wr = _bf(P["c1.weight"]).requires_grad_(True)
+    br = P["c1.bias"].clone().requires_grad_(True)
+    o = F.conv2d(xr, wr, br)
+    o.backward(gz)
+    assert rel(out_t(z), o.detach()) < 1e-2
+    assert rel(run.pgrad["c1.bias"].cpu(), br.grad) < 1e-2
+    assert rel(run.pgrad["c1.weight"].cpu(), wr.grad) < 2e-2
+    assert rel(out_t(run.grad_of(xm)), xr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("act,transposed,n_out", [(0, False, 192), (1, False, 256), (0, True, 128), (0, False, 577)])
+def test_linear(act, transposed, n_out):
+    g = torch.Generator().manual_seed(11 + n_out)
+    rows, n_in = 300, 128
+    x = _bf(torch.randn(rows, n_in, generator=g))
+    w = torch.randn(n_in, n_out, generator=g) * 0.1 if transposed else torch.randn(n_out, n_in, generator=g) * 0.1
+    b = None if transposed else torch.randn(n_out, generator=g)
+    P = {"w": w}
+    if b is not None:
+        P["b"] = b
+    run = _mk_run(P)
+    xm = to_mat(run, x)
+    y = run.linear(xm, "w", None if transposed else "b", act=act, transposed_weight=transposed,
+                   out_fp32=(n_out == 577))
+    gy = _bf(torch.randn(rows, n_out, generator=g))
+    set_grad(run, y, gy)
+    backward(run)
+    xr = x.clone().requires_grad_(True)
+    wr = _bf(w).requires_grad_(True)
+    br = b.clone().requires_grad_(True) if b is not None else None
+    o = xr @ wr if transposed else F.linear(xr, wr, br)
+    if act == 1:
+        o = F.relu(o)
+    o.backward(gy)
+    assert rel(out_t(y), o.detach()) < 1e-2
+    assert rel(out_t(run.grad_of(xm)), xr.grad) < 2e-2
+    assert rel(run.pgrad["w"].cpu(), wr.grad) < 2e-2
+    if br is not None:
+        assert rel(run.pgrad["b"].cpu(), br.grad) < 1e-2
+
+
+@pytest.mark.parametrize("C,x_fp32,with_add", [(512, True, True), (128, False, False), (2048, False, False)])
+def test_layernorm(C, x_fp32, with_add):
+    g = torch.Generator().manual_seed(C)
+    rows, period = 130, 26
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    if not x_fp32:
+        x = _bf(x)
+    P = {"ln.weight": torch.rand(C, generator=g) + 0.5, "ln.bias": torch.randn(C, generator=g) * 0.1}
+    add = torch.randn(period, C, generator=g) if with_add else None
+    run = _mk_run(P)
+    xm = to_mat(run, x, fp32=x_fp32)
+    y, y2 = run.layernorm(xm, "ln", add=add.cuda() if with_add else None, want_y=True, want_y2=with_add)
+    g1 = _bf(torch.randn(rows, C, generator=g))
+    g2 = _bf(torch.randn(rows, C, generator=g))
+    set_grad(run, y, g1)
+    if with_add:
+        set_grad(run, y2, g2)
+    backward(run)
+    xr = x.clone().requires_grad_(True)
+    wr = P["ln.weight"].clone().requires_grad_(True)
+    br = P["ln.bias"].clone().requires_grad_(True)
+    o = F.layer_norm(xr, (C,), wr, br, 1e-5)
+    loss = (o * g1).sum()
+    if with_add:
+        o2 = o + add.repeat(rows // period, 1)
+        loss = loss + (o2 * g2).sum()
+        assert rel(out_t(y2), o2.detach()) < 1e-2
+    loss.backward()
+    assert rel(out_t(y), o.detach()) < 1e-2
+    assert rel(out_t(run.grad_of(xm)), xr.grad) < 2e-2
+    assert rel(run.pgrad["ln.weight"].cpu(), wr.grad) < 2e-2
+    assert rel(run.pgrad["ln.bias"].cpu(), br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("Lq,Lk,heads,causal,key_pad", [(17, 17, 2, True, False), (100, 17, 2, False, True),
+                                                        (169, 169, 4, False, False), (676, 676, 2, False, False)])
+def test_attention(Lq, Lk, heads, causal, key_pad):
+    g = torch.Generator().manual_seed(Lq * 7 + Lk)
+    B, E = 2, heads * 64
+    q = _bf(torch.randn(B * Lq, E, generator=g))
+    k = _bf(torch.randn(B * Lk, E, generator=g))
+    v = _bf(torch.randn(B * Lk, E, generator=g))
+    run = _mk_run({})
+    word = torch.zeros(B, Lk, dtype=torch.long)
+    word[0, :9] = torch.arange(1, 10)
+    word[1, :5] = torch.arange(1, 6)
+    run.word = word.cuda()
+    qm, km, vm = to_mat(run, q), to_mat(run, k), to_mat(run, v)
+    o = run.attention(qm, km, vm, B, heads, Lq, Lk, causal=causal, key_pad=key_pad)
+    go = _bf(torch.randn(B * Lq, E, generator=g))
+    set_grad(run, o, go)
+    backward(run)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    qh = qr.view(B, Lq, heads, 64).transpose(1, 2)
+    kh = kr.view(B, Lk, heads, 64).transpose(1, 2)
+    vh = vr.view(B, Lk, heads, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if causal:
+        s = s + torch.full((Lq, Lk), float("-inf")).triu_(1)
+    if key_pad:
+        s = s.masked_fill((word == 0)[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Lq, E)
+    ref.backward(go)
+    assert rel(out_t(o), ref.detach()) < 1.5e-2
+    assert rel(out_t(run.grad_of(vm)), vr.grad) < 2.5e-2
+    assert rel(out_t(run.grad_of(qm)), qr.grad) < 3e-2
+    assert rel(out_t(run.grad_of(km)), kr.grad) < 3e-2
+
+
+def test_avgpool_upsample():
+    g = torch.Generator().manual_seed(3)
+    N, C, H, W = 2, 64, 8, 6
+    x = _bf(torch.randn(N, C, H, W, generator=g))
+    run = _mk_run({})
+    xm = to_padded(run, x)
+    yp = run.avgpool(xm)
+    yu = run.upsample(xm)
+    gp = _bf(torch.randn(N, C, H // 2, W // 2, generator=g))
+    gu = _bf(torch.randn(N, C, 2 * H, 2 * W, generator=g))
+    set_grad(run, yp, gp)
+    set_grad(run, yu, gu)
+    backward(run)
+    xr = x.clone().requires_grad_(True)
+    a = F.avg_pool2d(xr, 2)
+    b = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    ((a * gp).sum() + (b * gu).sum()).backward()
+    assert rel(out_t(yp), a.detach()) < 5e-3
+    assert rel(out_t(yu), b.detach()) < 5e-3
+    assert rel(out_t(run.grad_of(xm)), xr.grad) < 1e-2
+
+
+def test_dynconv_bce():
+    from cris.pytorch_b200.engine import Mat
+    from cris.pytorch_b200._lib import call
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 3, 64, 12, 10
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    t = torch.randn(B, 9 * C + 1, generator=g) * 0.05
+    mask = torch.rand(B, 1, 4 * H, 4 * W, generator=g)
+    run = _mk_run({})
+    xm = to_padded(run, x)
+    ld = (9 * C + 1 + 7) // 8 * 8
+    tb = torch.zeros(B, ld, device="cuda")
+    tb[:, :9 * C + 1] = t.cuda()
+    pred = torch.empty(B, 1, H, W, device="cuda")
+    mo = torch.empty(B, 1, H, W, device="cuda")
+    loss = torch.zeros((), device="cuda")
+    mk = mask.cuda()
+    call("cris_dynconv_bce_fwd", xm.ptr, xm.ld, tb.data_ptr(), ld, mk.data_ptr(), 4 * H, 4 * W, pred.data_ptr(),
+         mo.data_ptr(), loss.data_ptr(), B, H, W, C)
+    xr = x.clone().requires_grad_(True)
+    tr = t.clone().requires_grad_(True)
+    kern, bias = tr[:, :-1].reshape(B, C, 3, 3), tr[:, -1]
+    patches = F.unfold(xr, 3, padding=1).view(B, C * 9, H * W)
+    ref = (torch.einsum("bkp,bk->bp", patches, kern.reshape(B, C * 9)) + bias[:, None]).view(B, 1, H, W)
+    tgt = mask[:, :, ::4, ::4]
+    rl = F.binary_cross_entropy_with_logits(ref, tgt)
+    (rl * 3.0).backward()
+    assert rel(pred.cpu(), ref.detach()) < 1e-3
+    assert torch.equal(mo.cpu(), tgt)
+    assert abs(float(loss) - float(rl)) < 1e-4
+    gs = torch.full((1,), 3.0, device="cuda")
+    dl = torch.empty(B * H * W, device="cuda")
+    dx = torch.empty(B * (H + 2) * (W + 2), C, dtype=torch.bfloat16, device="cuda")
+    dt = torch.zeros(B, ld, device="cuda")
+    call("cris_dynconv_bce_bwd", xm.ptr, xm.ld, tb.data_ptr(), ld, pred.data_ptr(), mo.data_ptr(), gs.data_ptr(),
+         dl.data_ptr(), dx.data_ptr(), C, dt.data_ptr(), ld, B, H, W, C)
+    torch.cuda.synchronize()
+    dxm = Mat(dx, dx.shape[0], C, geom=(B, H, W))
+    assert rel(out_t(dxm), xr.grad) < 1e-2
+    assert rel(dt[:, :9 * C + 1].cpu(), tr.grad) < 1e-2
+
+
+def test_residual_dropout_statistics():
+    run = _mk_run({}, p_drop=0.1)
+    x = torch.zeros(4096, 512)
+    h = torch.ones(4096, 512)
+    out = run.residual_add(to_mat(run, x, fp32=True), to_mat(run, h), 0.1)
+    o = out_t(out)
+    keep = (o > 0).float().mean().item()
+    assert abs(keep - 0.9) < 5e-3
+    assert abs(o[o > 0].mean().item() - 1 / 0.9) < 1e-2
+    hm = out  # grad path: same mask must be regenerated
+    set_grad(run, out, torch.ones(4096, 512))
+    backward(run)
+
+
+def test_stem_and_embed():
+    from cris.pytorch_b200._lib import call
+    from cris.pytorch_b200.engine import Mat
+    g = torch.Generator().manual_seed(21)
+    B, Hin = 2, 32
+    img = torch.randn(B, 3, Hin, Hin, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    z = torch.empty(B * 18 * 18, 32, dtype=torch.bfloat16, device="cuda")
+    ic, wc = img.cuda(), w.cuda()
+    call("cris_stem_conv1_fwd", ic.data_ptr(), wc.data_ptr(), z.data_ptr(), 32, B, Hin, Hin, 32)
+    ref = F.conv2d(img, w, stride=2, padding=1)
+    zm = Mat(z, z.shape[0], 32, geom=(B, 16, 16))
+    assert rel(out_t(zm), ref) < 5e-3
+    gz = _bf(torch.randn(B, 32, 16, 16, generator=g))
+    gzp = torch.zeros(B, 18, 18, 32, dtype=torch.bfloat16, device="cuda")
+    gzp[:, 1:-1, 1:-1, :] = gz.permute(0, 2, 3, 1).cuda().to(torch.bfloat16)
+    dw = torch.zeros(32, 27, device="cuda")
+    call("cris_stem_conv1_wgrad", ic.data_ptr(), gzp.data_ptr(), 32, dw.data_ptr(), B, Hin, Hin, 32)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(img, wr, stride=2, padding=1).backward(gz)
+    assert rel(dw.cpu().view_as(w), wr.grad) < 1e-2
+    # embedding + EOT gather
+    L, E, V = 17, 128, 50
+    word = torch.randint(1, V, (B, L), generator=g)
+    word[:, 9:] = 0
+    word[0, 8] = V - 1
+    word[1, 5] = V - 1
+    table = torch.randn(V, E, generator=g)
+    pos = torch.randn(77, E, generator=g)
+    x = torch.empty(B * L, E, device="cuda")
+    wd, tc, pc = word.cuda(), table.cuda(), pos.cuda()
+    call("cris_embed_fwd", wd.data_ptr(), tc.data_ptr(), pc.data_ptr(), x.data_ptr(), B, L, E)
+    assert rel(x.cpu(), (table[word] + pos[:L]).reshape(B * L, E)) < 1e-6
+    out = torch.empty(B, E, dtype=torch.bfloat16, device="cuda")
+    call("cris_eot_gather", wd.data_ptr(), x.data_ptr(), 1, E, out.data_ptr(), E, B, L, E)
+    exp = (table[word] + pos[:L])[torch.arange(B), word.argmax(-1)]
+    assert rel(out.float().cpu(), exp) < 5e-3

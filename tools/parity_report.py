@@ -40,7 +40,9 @@ def main():
     arch = sys.argv[1] if len(sys.argv) > 1 else "tiny"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     size = int(sys.argv[3]) if len(sys.argv) > 3 else (128 if arch == "tiny" else 416)
-    torch.set_num_threads(os.cpu_count() or 8)
+    from oracle.hostinfo import usable_cpus
+    torch.set_num_threads(min(32, usable_cpus()))
+    print(f"[host] usable cpus {usable_cpus()} (os.cpu_count {os.cpu_count()})")
     cfg, sd, model = build(arch)
     img, word, mask = synth.make_inputs(B, 0, size, cfg.word_len, synth.ARCHS[arch]["vocab"])
     model = model.cuda()
@@ -73,9 +75,10 @@ def main():
            for k, v in sd.items()}
     otaps = {}
     t0 = time.time()
-    ref = O.cris_forward(sdg, img, word, mask, training=True, num_head=cfg.num_head, taps=otaps)
+    storage = os.environ.get("PARITY_STORAGE", "bf16")
+    ref = O.cris_forward(sdg, img, word, mask, training=True, num_head=cfg.num_head, taps=otaps, storage=storage)
     ref["loss"].backward()
-    print(f"[train] oracle fwd+bwd {time.time() - t0:.1f}s")
+    print(f"[train] oracle ({storage} storage) fwd+bwd {time.time() - t0:.1f}s")
     model.train()
     eng.debug_taps = {}
     pred, m, loss = model(img.cuda(), word.cuda(), mask.cuda())
@@ -100,7 +103,7 @@ def main():
         r = rel(prm.grad.cpu(), g_ref)
         worst.append((r, k, float(g_ref.norm())))
     worst.sort(reverse=True)
-    for r, k, n in worst[:25]:
+    for r, k, n in (worst if os.environ.get("PARITY_ALL") else worst[:25]):
         print(f"[grad] {r:.3e}  |ref| {n:.3e}  {k}")
     import statistics
     print(f"[grad] median rel err {statistics.median([w[0] for w in worst]):.3e} over {len(worst)} tensors")
