@@ -148,6 +148,10 @@ class Engine:
         self.consts: Dict[tuple, torch.Tensor] = {}
         self.step = 0
         self.debug_taps: Optional[dict] = None  # set to {} to collect named intermediates (tests only)
+        # bench.py: CUDA-event pairs recorded around the forward GEMM launch of one named convolution, so the
+        # dominant kernel is timed live inside the timed step (on the stream it is launched on)
+        self.probe_name: Optional[str] = None
+        self.probe_events: List = []
         _lib.lib()
 
     def const(self, key, fn, device):
@@ -434,9 +438,16 @@ class Run:
         part = self.f32(n_tiles * 2 * cout) if stats else None
         bias = self.P[bias_name].data_ptr() if bias_name else None
         offs = self.taps_of(x.geom) if k == 3 else None
+        probe = self.e.probe_name == wname
+        if probe:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         self.gemm(x, wp, z, x.rows, cout, cin, bias=bias, mask_geom=x.geom,
                   colstats=part.data_ptr() if stats else None, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE,
                   taps=9 if k == 3 else 1, tap_off=offs, b_tap_k=cin_pad if k == 3 else 0)
+        if probe:
+            ev1.record()
+            self.e.probe_events.append((ev0, ev1))
 
         def bwd():
             dz = self.grad_of(z)
@@ -802,9 +813,10 @@ class Run:
         heads = E // 64
         x = self.new(B * L, E, True)
         call("cris_embed_fwd", self.word.data_ptr(), table.data_ptr(), pos.data_ptr(), x.ptr, B, L, E)
+        x_embed = x  # `x` is rebound by the residual blocks below; closures must capture the embedding output
 
         def bwd_embed():
-            g = self.grad_of(x)
+            g = self.grad_of(x_embed)
             if g is None:
                 return
             call("cris_embed_bwd", self.word.data_ptr(), g.ptr, self.pg(b + ".token_embedding.weight").data_ptr(),
@@ -929,9 +941,10 @@ class Run:
         tpos = self.e.const(("pos1d", C, L, B), lambda: _pos1d(C, L).repeat(B, 1), self.dev)
         vis = self.new(B * T, C, True)
         call("cris_padded_to_tokens", fq.ptr, fq.ld, None, 0, vis.ptr, 1, vis.ld, B, H, W, C)
+        vis_in = vis  # `vis` is rebound by every decoder layer; the closure needs the first one
 
         def bwd_vis():
-            g = self.grad_of(vis)
+            g = self.grad_of(vis_in)
             if g is None:
                 return
             slot, acc = self.grad_slot(fq)

@@ -1,0 +1,190 @@
+"""GPU: whole-model parity of cris.pytorch_b200 (hand-written sm_100a kernels, called through the C ABI)
+against (a) the CPU fp32 oracle, (b) the oracle with the engine's bf16 storage points emulated and (c) the
+committed golden outputs of the unmodified reference.
+
+Stated tolerances (north_star: "outputs matching the reference PyTorch forward ... to a stated fp tolerance"):
+  eval logits      : relative L2 error <= 2e-2 vs fp32 (bf16 tensor-core operands, fp32 accumulate)
+  thresholded mask : a pixel may only differ from the fp32 mask if its fp32 logit is within 0.05 of the
+                     threshold logit(0.35) = -0.619 (pixels farther away must match bit-exactly)
+  train loss       : |delta| <= 5e-3 vs the bf16-storage oracle, <= 2e-2 vs fp32
+  gradients        : cosine similarity of the concatenated gradient >= 0.9 vs autograd of the bf16-storage
+                     oracle (ReLU-mask flips between two bf16 trajectories bound what any bf16 path can reach);
+                     the per-kernel forward/backward checks at 1-4 % live in tests/test_ops_gpu.py
+"""
+import os
+import tempfile
+
+import pytest
+import torch
+
+from oracle import cris_oracle as O
+from oracle import synth
+from oracle.hostinfo import usable_cpus
+
+pytestmark = pytest.mark.gpu
+THR = -0.6190392
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(arch, dropout=0.0):
+    from cris.pytorch_b200 import CRIS
+    cfg = synth.make_cfg(arch, dropout=dropout)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "clip.pt")
+        synth.save_clip_torchscript(synth.clip_state_dict(arch, 0), path)
+        cfg.clip_pretrain = path
+        model = CRIS(cfg)
+    sd = synth.full_state_dict(arch, 0, cfg)
+    model.load_state_dict(sd, strict=True)
+    return cfg, sd, model.cuda()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    torch.set_num_threads(min(16, usable_cpus()))
+    return build("tiny")
+
+
+def test_native_library_is_the_path(tiny):
+    from cris.pytorch_b200 import _lib
+    cfg, sd, model = tiny
+    img, word, _ = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    n0 = _lib.launch_count()
+    model.eval()
+    with torch.no_grad():
+        model(img.cuda(), word.cuda())
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 > 250  # every op of the forward is one of our kernels
+    with pytest.raises(RuntimeError):
+        model(img, word)  # CPU tensors: there is no CPU fallback
+
+
+def test_eval_forward_matches_fp32_oracle(tiny):
+    cfg, sd, model = tiny
+    img, word, _ = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    with torch.no_grad():
+        ref = O.cris_forward(sd, img, word, training=False, num_head=cfg.num_head)["pred"]
+        model.eval()
+        pred = model(img.cuda(), word.cuda()).cpu()
+    assert pred.shape == ref.shape
+    assert rel(pred, ref) <= 2e-2
+    flips = (pred > THR) != (ref > THR)
+    assert int((flips & ((ref - THR).abs() > 0.05)).sum()) == 0
+    assert float(flips.float().mean()) < 0.02
+
+
+def test_eval_matches_reference_golden(tiny, golden_dir):
+    cfg, sd, model = tiny
+    g = torch.load(os.path.join(golden_dir, "tiny_b2_128.pt"), weights_only=False)
+    img, word, _ = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    model.eval()
+    with torch.no_grad():
+        pred = model(img.cuda(), word.cuda()).cpu()
+    assert rel(pred, g["eval_pred"]) <= 2e-2
+    a, b = pred > THR, g["eval_pred"] > THR
+    iou = float((a & b).sum()) / max(1.0, float((a | b).sum()))
+    assert iou >= 0.97
+
+
+def test_train_step_matches_oracle(tiny):
+    cfg, sd, model = tiny
+    model.load_state_dict(sd, strict=True)
+    img, word, mask = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    ref = O.cris_forward(sdg, img, word, mask, training=True, num_head=cfg.num_head, storage="bf16")
+    ref["loss"].backward()
+    with torch.no_grad():
+        ref32 = O.cris_forward(sd, img, word, mask, training=True, num_head=cfg.num_head)
+    model.train()
+    model.zero_grad(set_to_none=True)
+    pred, m, loss = model(img.cuda(), word.cuda(), mask.cuda())
+    assert torch.equal(m.cpu(), ref["mask"])
+    assert abs(float(loss) - float(ref["loss"])) <= 5e-3
+    assert abs(float(loss) - float(ref32["loss"])) <= 2e-2
+    assert rel(pred.cpu(), ref["pred"].detach()) <= 8e-2
+    assert not pred.requires_grad and loss.requires_grad
+    loss.backward()
+    mine, theirs = [], []
+    for k, p in model.named_parameters():
+        if k == "backbone.logit_scale":
+            assert p.grad is None and sdg[k].grad is None
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if "txt_proj.1" in k:  # BatchNorm1d over a batch of 2 is a sign function: chaotic by construction
+            continue
+        mine.append(p.grad.flatten().cpu().double())
+        theirs.append(sdg[k].grad.flatten().double())
+    a, b = torch.cat(mine), torch.cat(theirs)
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    assert cos >= 0.9, cos
+    assert 0.8 <= float(a.norm() / b.norm()) <= 1.25
+    # BatchNorm running statistics were updated like nn.BatchNorm2d(momentum=0.1) does
+    msd = model.state_dict()
+    worst = max(rel(msd[k].cpu(), v) for k, v in ref["new_running"].items() if "txt_proj" not in k)
+    assert worst <= 8e-2
+    assert int(msd["backbone.visual.bn1.num_batches_tracked"]) >= 1
+
+
+def test_training_reduces_loss_and_state_dict_roundtrip(tiny):
+    cfg, sd, model = tiny
+    model.load_state_dict(sd, strict=True)
+    img, word, mask = synth.make_inputs(4, 3, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    img, word, mask = img.cuda(), word.cuda(), mask.cuda()
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(12):
+        _, _, loss = model(img, word, mask)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] - 0.02, losses
+    out = model.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    assert all(out[k].shape == sd[k].shape and out[k].dtype == sd[k].dtype for k in sd)
+
+
+def test_dropout_path_runs(tiny):
+    """cfg.dropout = 0.1 (the yaml default): statistical check only — masks cannot match torch's Philox stream."""
+    cfg, sd, _ = tiny
+    _, _, model = build("tiny", dropout=0.1)
+    img, word, mask = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    model.train()
+    _, _, l1 = model(img.cuda(), word.cuda(), mask.cuda())
+    l1.backward()
+    _, _, l2 = model(img.cuda(), word.cuda(), mask.cuda())
+    assert torch.isfinite(l1) and torch.isfinite(l2)
+    assert float(l1) != float(l2)  # different dropout masks per step
+    assert abs(float(l1) - float(l2)) < 0.2
+
+
+def test_r50_matches_reference_golden(golden_dir):
+    """Full-size cris_r50 (416x416, 17 tokens, B=2) against the committed outputs of the unmodified reference."""
+    g = torch.load(os.path.join(golden_dir, "r50_b2_416.pt"), weights_only=False)
+    cfg, sd, model = build("r50")
+    img, word, mask = synth.make_inputs(2, 0, 416, cfg.word_len, synth.ARCHS["r50"]["vocab"])
+    model.eval()
+    with torch.no_grad():
+        pred = model(img.cuda(), word.cuda()).cpu()
+    assert pred.shape == (2, 1, 104, 104)
+    assert rel(pred, g["eval_pred"]) <= 3e-2
+    ref = g["eval_pred"]
+    flips = (pred > THR) != (ref > THR)
+    assert int((flips & ((ref - THR).abs() > 0.05)).sum()) == 0
+    a, b = pred > THR, ref > THR
+    assert float((a & b).sum()) / max(1.0, float((a | b).sum())) >= 0.95
+    model.train()
+    p2, m2, loss = model(img.cuda(), word.cuda(), mask.cuda())
+    assert torch.equal(m2.cpu(), g["train_mask"])
+    assert abs(float(loss) - float(g["train_loss"])) <= 3e-2
+    loss.backward()
+    gn = {k: float(p.grad.double().norm()) for k, p in model.named_parameters() if p.grad is not None}
+    # gradient norms of the head (closest to the loss) agree with the reference's within bf16 noise
+    for k in ("proj.txt.weight", "proj.vis.4.weight", "proj.vis.4.bias"):
+        assert abs(gn[k] - float(g["grads"][k]["norm"])) <= 0.15 * float(g["grads"][k]["norm"]), k
