@@ -349,19 +349,23 @@ static int run_case(const Case& cs) {
   return fail;
 }
 
-static void perf() {
+static void perf(int only = -1) {
   struct P { const char* name; int M, N, K, taps, hp, wp, a_mn, b_mn; };
   const P ps[] = {
       {"lin 43264x512x512", 43264, 512, 512, 1, 0, 0, 0, 0},
       {"lin 43264x2048x512", 43264, 2048, 512, 1, 0, 0, 0, 0},
       {"gemm 8192^3", 8192, 8192, 8192, 1, 0, 0, 0, 0},
+      {"conv3x3 64x(106x106) 512->256", 64 * 106 * 106, 256, 512, 9, 106, 106, 0, 0},
       {"conv3x3 64x(54x54) 512->512", 64 * 54 * 54, 512, 512, 9, 54, 54, 0, 0},
       {"conv3x3 64x(106x106) 64->64", 64 * 106 * 106, 64, 64, 9, 106, 106, 0, 0},
       {"conv1x1 64x(106x106) 256->64", 64 * 106 * 106, 64, 256, 1, 106, 106, 0, 0},
       {"dgrad 43264x512x2048 (B MN)", 43264, 512, 2048, 1, 0, 0, 0, 1},
       {"wgrad 512x512x43264 (A,B MN)", 512, 512, 43264, 1, 0, 0, 1, 1},
   };
+  int pi = -1;
   for (const P& q : ps) {
+    ++pi;
+    if (only >= 0 && pi != only) continue;
     cris_gemm_args a; memset(&a, 0, sizeof(a));
     a.M = q.M; a.N = q.N; a.K = q.K; a.batch = 1; a.alpha = 1.f; a.splits = 1; a.a_mn = q.a_mn; a.b_mn = q.b_mn;
     a.taps = q.taps; a.tap_mode = q.taps > 1 ? 1 : 0;
@@ -394,7 +398,7 @@ int main(int argc, char** argv) {
   auto cases = make_cases();
   if (argc < 2 || !strcmp(argv[1], "list")) { printf("%zu\n", cases.size()); return 0; }
   if (cris_device_check() != 0) { printf("device check failed: %s\n", cris_last_error()); return 2; }
-  if (!strcmp(argv[1], "perf")) { perf(); return 0; }
+  if (!strcmp(argv[1], "perf")) { perf(argc > 2 ? atoi(argv[2]) : -1); return 0; }
   int i = atoi(argv[1]);
   if (i < 0 || i >= (int)cases.size()) return 2;
   return run_case(cases[i]);

@@ -17,6 +17,7 @@ def _mk_run(params=None, buffers=None, training=True, p_drop=0.0):
             self.packed = E.PackedWeights()
             self.consts = {}
             self.debug_taps = None
+            self.probe_name, self.probe_events = None, []
             self.step = 0
 
         const = E.Engine.const
