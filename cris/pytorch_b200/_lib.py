@@ -60,6 +60,7 @@ _SIGS = {
     "cris_padded_to_tokens": "pqpqpiqiiiip",
     "cris_tokens_to_padded": "piqpqiiiip",
     "cris_coord_fill": "pqiiiip",
+    "cris_stem_im2col": "ppiiip",
     "cris_stem_conv1_fwd": "pppqiiiip",
     "cris_stem_conv1_wgrad": "ppqpiiiip",
     "cris_softmax_fwd": "pppqqiiiipifup",

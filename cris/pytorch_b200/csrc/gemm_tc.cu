@@ -216,9 +216,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
         continue;
       }
       if (p.bias != nullptr) {
+        const float* bp = p.bias + ncol0;
+        if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (ncol0 + j < p.N) v[j] += __ldg(p.bias + ncol0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(bp + j));
+            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ncol0 + j < p.N) v[j] += __ldg(bp + j);
+        }
       }
       if (p.act != CRIS_ACT_NONE) {
 #pragma unroll
@@ -227,14 +236,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
       if (p.resid != nullptr && row_in) {
         if (p.resid_fp32) {
           const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
+          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ncol0 + j < p.N) v[j] += rp[j];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ncol0 + j < p.N) v[j] += rp[j];
+          }
         } else {
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
+          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+              const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c2 = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+              v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
+              v[j + 4] += c2.x; v[j + 5] += c2.y; v[j + 6] += d.x; v[j + 7] += d.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
+          }
         }
       }
       if (!row_valid) {

@@ -100,18 +100,31 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_tiles, int C2,
-                                       float* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C2) return;
-  float s = 0.f, comp = 0.f;  // Kahan: thousands of tile partials per channel
-  for (int t = 0; t < n_tiles; ++t) {
-    const float v = partials[(size_t)t * C2 + i] - comp;
-    const float ns = s + v;
-    comp = (ns - s) - v;
-    s = ns;
+// sums[i] = sum_t partials[t][i]: 32 columns x 8 tile-lanes per block, coalesced 128 B rows, fp32 tree
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_tiles, int C2,
+                                                              float* __restrict__ sums) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // 4 independent chains for ILP
+  if (i < C2) {
+    int t = grp;
+    for (; t + 24 < n_tiles; t += 32) {
+      s0 += partials[(size_t)t * C2 + i];
+      s1 += partials[(size_t)(t + 8) * C2 + i];
+      s2 += partials[(size_t)(t + 16) * C2 + i];
+      s3 += partials[(size_t)(t + 24) * C2 + i];
+    }
+    for (; t < n_tiles; t += 8) s0 += partials[(size_t)t * C2 + i];
   }
-  sums[i] = s;
+  sm[grp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0 && i < C2) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += sm[g][lane];
+    sums[i] = s;
+  }
 }
 
 __global__ void bn_coeffs_kernel(const float* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -370,8 +383,8 @@ int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void
 }
 
 int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums, void* stream) {
-  reduce_partials_kernel<<<(2 * C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles,
-                                                                                                 2 * C, sums);
+  reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles,
+                                                                                               2 * C, sums);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -346,6 +346,37 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < 27; ++k) atomicAdd(dw + co * 27 + k, acc[k]);
 }
 
+// ---- stem im2col: fp32 NCHW image -> bf16 patches [N, H/2+2, W/2+2, 32] (27 taps (ci,ky,kx) of the 3x3 stride-2
+// pad-1 stem convolution + 5 zero channels), so that conv1 and its wgrad run on the tcgen05 GEMM core.
+__global__ void __launch_bounds__(256)
+    stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int Hin, int Win) {
+  const int Ho = Hin / 2, Wo = Win / 2;
+  const int hp = Ho + 2, wp = Wo + 2;
+  const long long total = (long long)N * hp * wp * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 3);
+    const long long r = i >> 2;
+    const int wq = (int)(r % wp);
+    const int hq = (int)((r / wp) % hp);
+    const int n = (int)(r / ((long long)wp * hp));
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (hq >= 1 && hq <= Ho && wq >= 1 && wq <= Wo) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = g * 8 + k;
+        if (t < 27) {
+          const int ci = t / 9, ky = (t % 9) / 3, kx = t % 3;
+          const int hi = 2 * (hq - 1) + ky - 1, wi = 2 * (wq - 1) + kx - 1;
+          if (hi >= 0 && hi < Hin && wi >= 0 && wi < Win)
+            o[k] = __ldg(img + (((long long)n * 3 + ci) * Hin + hi) * Win + wi);
+        }
+      }
+    }
+    st8(out + r * 32 + g * 8, o);
+  }
+}
+
 }  // namespace cris
 
 using namespace cris;
@@ -420,6 +451,13 @@ int cris_tokens_to_padded(const void* tok, int tok_fp32, int64_t ldt, void* y, i
 int cris_coord_fill(void* buf, int64_t ld, int c0, int N, int H, int W, void* stream) {
   CRIS_CHECK_ARG(c0 % 8 == 0, "coord_fill: c0=%d must be a multiple of 8", c0);
   coord_fill_kernel<<<grid_for((long long)N * (H + 2) * (W + 2), 256), 256, 0, STREAM>>>(BF(buf), ld, c0, N, H, W);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_stem_im2col(const float* img, void* out, int N, int Hin, int Win, void* stream) {
+  CRIS_CHECK_ARG(Hin % 2 == 0 && Win % 2 == 0, "stem_im2col: odd image size");
+  const long long work = (long long)N * (Hin / 2 + 2) * (Win / 2 + 2) * 4;
+  stem_im2col_kernel<<<grid_for(work, 256, 148 * 32), 256, 0, STREAM>>>(img, BF(out), N, Hin, Win);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -8,9 +8,10 @@
 namespace cris {
 
 // ---- softmax over rows of S[nb][Lq][ld] (scores already scaled by the GEMM alpha) ----------------
-// One warp per row; Lk <= 32*MAXE.  causal: key j > query i masked.  key padding: token id word[b][j] == 0
-// masked (pad_mask of model/segmenter.py:37), b = batch_index / heads.  P (bf16) = softmax; Pd (optional) = dropout(P) * 1/(1-p).
-template <int MAXE>
+// One warp per row, 16-byte vector accesses: lane handles 8 consecutive keys per vector, NV vectors per lane
+// (Lk <= 256*NV; ld % 8 == 0).  causal: key j > query i masked.  key padding: token id word[b][j] == 0 masked
+// (pad_mask of model/segmenter.py:37), b = batch_index / heads.  P = softmax; Pd (optional) = dropout(P)/(1-p).
+template <int NV>
 __global__ void __launch_bounds__(256)
     softmax_fwd_kernel(const __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ P,
                        __nv_bfloat16* __restrict__ Pd, long long ld, long long batch_stride, int nb, int Lq, int Lk,
@@ -21,43 +22,50 @@ __global__ void __launch_bounds__(256)
   const int bi = (int)(rid / Lq), qi = (int)(rid % Lq);
   const long long off = (long long)bi * batch_stride + (long long)qi * ld;
   const long long* km = kpm ? kpm + (long long)(bi / heads) * Lk : nullptr;  // token ids; id 0 = padding
-  float v[MAXE];
+  float v[NV][8];
   float mx = -INFINITY;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = e * 32 + lane;
-    float x = -INFINITY;
-    if (j < Lk) {
-      x = bf2f(S[off + j]);
-      if ((causal && j > qi) || (km && km[j] == 0)) x = -INFINITY;
+  for (int e = 0; e < NV; ++e) {
+    const int j0 = (e * 32 + lane) * 8;
+    if (j0 < ld) ld8(S + off + j0, v[e]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + i;
+      if (j >= Lk || (causal && j > qi) || (km && km[j] == 0)) v[e][i] = -INFINITY;
+      mx = fmaxf(mx, v[e][i]);
     }
-    v[e] = x;
-    mx = fmaxf(mx, x);
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    v[e] = (v[e] == -INFINITY) ? 0.f : __expf(v[e] - mx);
-    sum += v[e];
-  }
+  for (int e = 0; e < NV; ++e)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[e][i] = (v[e][i] == -INFINITY) ? 0.f : __expf(v[e][i] - mx);
+      sum += v[e][i];
+    }
   sum = warp_sum(sum);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
   const uint32_t th = drop_thresh(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = e * 32 + lane;
-    if (j < Lk) {
-      const float pr = v[e] * inv;
-      P[off + j] = f2bf(pr);
-      if (Pd != nullptr) Pd[off + j] = f2bf(drop_keep(seed, (uint64_t)(off + j), th) ? pr * keep_scale : 0.f);
+  for (int e = 0; e < NV; ++e) {
+    const int j0 = (e * 32 + lane) * 8;
+    if (j0 < ld) {
+      float pr[8], pd[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pr[i] = v[e][i] * inv;
+        pd[i] = (Pd != nullptr && drop_keep(seed, (uint64_t)(off + j0 + i), th)) ? pr[i] * keep_scale : 0.f;
+      }
+      st8(P + off + j0, pr);
+      if (Pd != nullptr) st8(Pd + off + j0, pd);
     }
   }
 }
 
 // dS = P * (dPm - sum_j P*dPm), dPm = dP * dropmask/(1-p);  written in place of dP (bf16)
-template <int MAXE>
+template <int NV>
 __global__ void __launch_bounds__(256)
     softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dP, long long ld,
                        long long batch_stride, int nb, int Lq, int Lk, float p_drop, uint64_t seed) {
@@ -68,25 +76,34 @@ __global__ void __launch_bounds__(256)
   const long long off = (long long)bi * batch_stride + (long long)qi * ld;
   const uint32_t th = drop_thresh(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  float pv[MAXE], dv[MAXE];
+  float pv[NV][8], dv[NV][8];
   float dot = 0.f;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = e * 32 + lane;
-    pv[e] = dv[e] = 0.f;
-    if (j < Lk) {
-      pv[e] = bf2f(P[off + j]);
-      float d = bf2f(dP[off + j]);
-      if (p_drop > 0.f) d = drop_keep(seed, (uint64_t)(off + j), th) ? d * keep_scale : 0.f;
-      dv[e] = d;
-      dot += pv[e] * d;
+  for (int e = 0; e < NV; ++e) {
+    const int j0 = (e * 32 + lane) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[e][i] = dv[e][i] = 0.f;
+    if (j0 < ld) {
+      ld8(P + off + j0, pv[e]);
+      ld8(dP + off + j0, dv[e]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (j0 + i >= Lk) { pv[e][i] = 0.f; dv[e][i] = 0.f; }
+        else if (p_drop > 0.f) dv[e][i] = drop_keep(seed, (uint64_t)(off + j0 + i), th) ? dv[e][i] * keep_scale : 0.f;
+        dot += pv[e][i] * dv[e][i];
+      }
     }
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = e * 32 + lane;
-    if (j < Lk) dP[off + j] = f2bf(pv[e] * (dv[e] - dot));
+  for (int e = 0; e < NV; ++e) {
+    const int j0 = (e * 32 + lane) * 8;
+    if (j0 < ld) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pv[e][i] * (dv[e][i] - dot);
+      st8(dP + off + j0, o);
+    }
   }
 }
 
@@ -276,30 +293,27 @@ extern "C" {
 int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
                      int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, void* stream) {
   const long long* kpm = reinterpret_cast<const long long*>(kpm_word);
-  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 32 * 22, "softmax: Lk=%d out of range (max 704)", Lk);
+  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 768 && ld % 8 == 0 && ld >= Lk && batch_stride % 8 == 0,
+                 "softmax: Lk=%d ld=%lld unsupported (Lk <= 768, ld %% 8 == 0)", Lk, (long long)ld);
   const int grid = (int)(((long long)nb * Lq + 7) / 8);
-  if (Lk <= 32)
+  if (Lk <= 256)
     softmax_fwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
                                                      causal, p_drop, seed);
-  else if (Lk <= 192)
-    softmax_fwd_kernel<6><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
-                                                     causal, p_drop, seed);
   else
-    softmax_fwd_kernel<22><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
-                                                      causal, p_drop, seed);
+    softmax_fwd_kernel<3><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
+                                                     causal, p_drop, seed);
   CRIS_LAUNCH_OK();
   return 0;
 }
 int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
                      uint64_t seed, void* stream) {
-  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 32 * 22, "softmax: Lk=%d out of range (max 704)", Lk);
+  CRIS_CHECK_ARG(Lk >= 1 && Lk <= 768 && ld % 8 == 0 && ld >= Lk && batch_stride % 8 == 0,
+                 "softmax: Lk=%d ld=%lld unsupported (Lk <= 768, ld %% 8 == 0)", Lk, (long long)ld);
   const int grid = (int)(((long long)nb * Lq + 7) / 8);
-  if (Lk <= 32)
+  if (Lk <= 256)
     softmax_bwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
-  else if (Lk <= 192)
-    softmax_bwd_kernel<6><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
   else
-    softmax_bwd_kernel<22><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+    softmax_bwd_kernel<3><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -74,13 +74,13 @@ class PackedWeights:
     def __init__(self):
         self.cache: Dict[str, tuple] = {}
 
-    def get(self, name: str, p: torch.Tensor) -> Mat:
+    def get(self, name: str, p: torch.Tensor, as_matrix: bool = False) -> Mat:
         ent = self.cache.get(name)
         key = (p._version, p.data_ptr())
         if ent is not None and ent[0] == key:
             return ent[1]
         w = p.detach()
-        if w.dim() == 4 and w.shape[2] == 3:
+        if w.dim() == 4 and w.shape[2] == 3 and not as_matrix:
             cout, cin = w.shape[0], w.shape[1]
             cp = _r8(cin)
             buf = ent[1].buf if ent is not None else torch.empty(cout, 9 * cp, dtype=torch.bfloat16, device=w.device)
@@ -248,8 +248,8 @@ class Run:
         self.n_seed += 1
         return (self.seed_base + self.n_seed * 104729) & ((1 << 63) - 1)
 
-    def w(self, name) -> Mat:
-        return self.e.packed.get(name, self.P[name])
+    def w(self, name, as_matrix=False) -> Mat:
+        return self.e.packed.get(name, self.P[name], as_matrix)
 
     def pg(self, name) -> torch.Tensor:
         g = self.pgrad.get(name)
@@ -426,13 +426,15 @@ class Run:
 
     # ---- convolution (implicit GEMM on tcgen05) ---------------------------------------------------
     def conv(self, x: Mat, wname: str, k: int, stats: bool, bias_name: Optional[str] = None,
-             cin: Optional[int] = None):
-        """z = conv_kxk(x) (stride 1, zero padding k//2), optional bias; returns (z, colstats partials, tiles)."""
-        wp = self.w(wname)
+             cin: Optional[int] = None, as_matrix: bool = False):
+        """z = conv_kxk(x) (stride 1, zero padding k//2), optional bias; returns (z, colstats partials, tiles).
+        as_matrix: the weight is used as a plain [Cout, Cin*kh*kw] matrix over pre-gathered patches (stem)."""
+        wp = self.w(wname, as_matrix)
         Wt = self.P[wname]
         cout = Wt.shape[0]
-        cin = Wt.shape[1] if cin is None else cin
-        cin_pad = _r8(Wt.shape[1])
+        w_cols = Wt.numel() // cout if as_matrix else Wt.shape[1]
+        cin = w_cols if cin is None else cin
+        cin_pad = _r8(w_cols)
         z = self.new(x.rows, cout, False, x.geom)
         n_tiles = (x.rows + 127) // 128
         part = self.f32(n_tiles * 2 * cout) if stats else None
@@ -457,7 +459,7 @@ class Run:
                 self.pg(bias_name).copy_(self.col_sum(dz, cout, z.hp, z.wp)[:cout])
             # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
             gw = self.pg(wname)
-            gwm = Mat(gw, cout, Wt.shape[1] * (9 if k == 3 else 1), fp32=True)
+            gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
             splits = self.wgrad_splits((cout + 127) // 128, (cin + 127) // 128, 9 if k == 3 else 1, x.rows)
             if k == 3:
                 self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
@@ -704,21 +706,13 @@ class Run:
         if Hin % 32 or Win % 32:
             raise ValueError("image size must be a multiple of 32")
         w1 = self.P[v + ".conv1.weight"]
-        c1 = w1.shape[0]
-        z = self.padded(B, Hin // 2, Win // 2, c1)
-        call("cris_stem_conv1_fwd", self.img.data_ptr(), w1.data_ptr(), z.ptr, z.ld, B, Hin, Win, c1)
-        z.need_grad = True
-
-        def bwd_stem():
-            dz = self.grad_of(z)
-            if dz is None:
-                return
-            gw = self.pg(v + ".conv1.weight")
-            call("cris_stem_conv1_wgrad", self.img.data_ptr(), dz.ptr, dz.ld, gw.data_ptr(), B, Hin, Win, c1)
-
-        if self.training:
-            self.on_backward(bwd_stem)
-        x = self.bn_forward(z, v + ".bn1", True)
+        # stem conv1 (3x3, stride 2) = im2col (27 taps, padded to 32) + the tcgen05 GEMM core (model/clip.py:165-170)
+        patches = self.padded(B, Hin // 2, Win // 2, 32)
+        call("cris_stem_im2col", self.img.data_ptr(), patches.ptr, B, Hin, Win)
+        patches.need_grad = False
+        z, part, nt = self.conv(patches, v + ".conv1.weight", 1, stats=self.training, cin=w1.numel() // w1.shape[0],
+                                as_matrix=True)
+        x = self.bn_forward(z, v + ".bn1", True, partials=part, n_tiles=nt)
         x = self.conv_bn(x, v + ".conv2.weight", v + ".bn2", 3)
         x = self.conv_bn(x, v + ".conv3.weight", v + ".bn3", 3)
         x = self.avgpool(x)

@@ -156,6 +156,8 @@ int cris_padded_to_tokens(const void* x, int64_t ldx, const float* add, int64_t 
 int cris_tokens_to_padded(const void* tok, int tok_fp32, int64_t ldt, void* y, int64_t ldy, int N, int H, int W, int C,
                           void* stream);
 int cris_coord_fill(void* buf, int64_t ld, int c0, int N, int H, int W, void* stream);
+/* fp32 NCHW image -> bf16 im2col patches [N, H/2+2, W/2+2, 32] of the 3x3/s2 stem conv (27 taps + 5 zeros) */
+int cris_stem_im2col(const float* img, void* out, int N, int Hin, int Win, void* stream);
 int cris_stem_conv1_fwd(const float* img, const float* w, void* z, int64_t ldz, int N, int Hin, int Win, int Cout,
                         void* stream);
 int cris_stem_conv1_wgrad(const float* img, const void* dz, int64_t lddz, float* dw, int N, int Hin, int Win, int Cout,

@@ -185,8 +185,8 @@ def encode_image(st: OracleState, img: Tensor):
     sd = st.sd
     v = "backbone.visual"
     q = st.q
-    # stem conv1 runs on the fp32 image with fp32 weights (its 27-tap kernel is not a tensor-core GEMM)
-    x = q(F.relu(batch_norm(st, q(F.conv2d(img, sd[v + ".conv1.weight"], stride=2, padding=1)), v + ".bn1")))
+    # stem conv1 = bf16 im2col patches x bf16 weights on the tensor cores (fp32 accumulate), like every conv
+    x = q(F.relu(batch_norm(st, q(F.conv2d(q(img), st.w(v + ".conv1.weight"), stride=2, padding=1)), v + ".bn1")))
     x = q(F.relu(batch_norm(st, q(F.conv2d(x, st.w(v + ".conv2.weight"), padding=1)), v + ".bn2")))
     x = q(F.relu(batch_norm(st, q(F.conv2d(x, st.w(v + ".conv3.weight"), padding=1)), v + ".bn3")))
     x = q(F.avg_pool2d(x, 2))
