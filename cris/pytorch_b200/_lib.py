@@ -63,13 +63,13 @@ _SIGS = {
     "cris_stem_im2col": "ppiiip",
     "cris_stem_conv1_fwd": "pppqiiiip",
     "cris_stem_conv1_wgrad": "ppqpiiiip",
-    "cris_softmax_fwd": "pppqqiiiipifup",
-    "cris_softmax_bwd": "ppqqiiifup",
+    "cris_softmax_fwd": "pppqqiiiipifupp",
+    "cris_softmax_bwd": "ppqqiiifupp",
     "cris_embed_fwd": "ppppiiip",
     "cris_embed_bwd": "ppppiiip",
     "cris_eot_gather": "ppiqpqiiip",
     "cris_eot_scatter": "ppiqpiqiiip",
-    "cris_elementwise": "ipiqpiqpiqqifup",
+    "cris_elementwise": "ipiqpiqpiqqifupp",
     "cris_pack_conv_weight": "ppiiiip",
     "cris_pack_matrix": "ppqiip",
     "cris_batch_reduce": "piqpqiiiip",

@@ -15,7 +15,9 @@ template <int NV>
 __global__ void __launch_bounds__(256)
     softmax_fwd_kernel(const __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ P,
                        __nv_bfloat16* __restrict__ Pd, long long ld, long long batch_stride, int nb, int Lq, int Lk,
-                       int heads, const long long* __restrict__ kpm, int causal, float p_drop, uint64_t seed) {
+                       int heads, const long long* __restrict__ kpm, int causal, float p_drop, uint64_t seed,
+                       const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed += *seed_dev;
   const int lane = threadIdx.x & 31;
   const long long rid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (rid >= (long long)nb * Lq) return;
@@ -68,7 +70,9 @@ __global__ void __launch_bounds__(256)
 template <int NV>
 __global__ void __launch_bounds__(256)
     softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ dP, long long ld,
-                       long long batch_stride, int nb, int Lq, int Lk, float p_drop, uint64_t seed) {
+                       long long batch_stride, int nb, int Lq, int Lk, float p_drop, uint64_t seed,
+                       const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed += *seed_dev;
   const int lane = threadIdx.x & 31;
   const long long rid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (rid >= (long long)nb * Lq) return;
@@ -189,7 +193,7 @@ struct EwArgs {
   const void* b; int b_fp32; long long ldb;
   void* out; int out_fp32; long long ldo;
   long long rows; int C;
-  float p_drop; uint64_t seed;
+  float p_drop; uint64_t seed; const uint64_t* seed_dev;
 };
 template <int OP>
 __global__ void ew_kernel(const EwArgs p) {
@@ -197,6 +201,7 @@ __global__ void ew_kernel(const EwArgs p) {
   const long long total = p.rows * G;
   const uint32_t th = drop_thresh(p.p_drop);
   const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  const uint64_t seed = p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / G;
@@ -208,8 +213,8 @@ __global__ void ew_kernel(const EwArgs p) {
     for (int k = 0; k < 4; ++k) {
       const uint64_t idx = (uint64_t)(r * p.C + c + k);
       if (OP == 0) o[k] = a[k] + b[k];
-      else if (OP == 1) o[k] = a[k] + ((p.p_drop > 0.f) ? (drop_keep(p.seed, idx, th) ? b[k] * ks : 0.f) : b[k]);
-      else if (OP == 2) o[k] = (p.p_drop > 0.f) ? (drop_keep(p.seed, idx, th) ? a[k] * ks : 0.f) : a[k];
+      else if (OP == 1) o[k] = a[k] + ((p.p_drop > 0.f) ? (drop_keep(seed, idx, th) ? b[k] * ks : 0.f) : b[k]);
+      else if (OP == 2) o[k] = (p.p_drop > 0.f) ? (drop_keep(seed, idx, th) ? a[k] * ks : 0.f) : a[k];
       else if (OP == 3) o[k] = a[k] / (1.f + __expf(-1.702f * a[k]));
       else if (OP == 4) {
         const float s = 1.f / (1.f + __expf(-1.702f * a[k]));
@@ -291,29 +296,30 @@ using namespace cris;
 extern "C" {
 
 int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
-                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, void* stream) {
+                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* stream) {
   const long long* kpm = reinterpret_cast<const long long*>(kpm_word);
   CRIS_CHECK_ARG(Lk >= 1 && Lk <= 768 && ld % 8 == 0 && ld >= Lk && batch_stride % 8 == 0,
                  "softmax: Lk=%d ld=%lld unsupported (Lk <= 768, ld %% 8 == 0)", Lk, (long long)ld);
   const int grid = (int)(((long long)nb * Lq + 7) / 8);
   if (Lk <= 256)
     softmax_fwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
-                                                     causal, p_drop, seed);
+                                                     causal, p_drop, seed, seed_dev);
   else
     softmax_fwd_kernel<3><<<grid, 256, 0, STREAM>>>(CBF(S), BF(P), BF(Pd), ld, batch_stride, nb, Lq, Lk, heads, kpm,
-                                                     causal, p_drop, seed);
+                                                     causal, p_drop, seed, seed_dev);
   CRIS_LAUNCH_OK();
   return 0;
 }
 int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
-                     uint64_t seed, void* stream) {
+                     uint64_t seed, const uint64_t* seed_dev, void* stream) {
   CRIS_CHECK_ARG(Lk >= 1 && Lk <= 768 && ld % 8 == 0 && ld >= Lk && batch_stride % 8 == 0,
                  "softmax: Lk=%d ld=%lld unsupported (Lk <= 768, ld %% 8 == 0)", Lk, (long long)ld);
   const int grid = (int)(((long long)nb * Lq + 7) / 8);
   if (Lk <= 256)
-    softmax_bwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+    softmax_bwd_kernel<1><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed, seed_dev);
   else
-    softmax_bwd_kernel<3><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed);
+    softmax_bwd_kernel<3><<<grid, 256, 0, STREAM>>>(CBF(P), BF(dP), ld, batch_stride, nb, Lq, Lk, p_drop, seed, seed_dev);
   CRIS_LAUNCH_OK();
   return 0;
 }
@@ -347,9 +353,10 @@ int cris_eot_scatter(const int64_t* word, const void* dout, int d_fp32, int64_t 
   return 0;
 }
 int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void* b, int b_fp32, int64_t ldb, void* out,
-                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, void* stream) {
+                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* stream) {
   CRIS_CHECK_ARG(C % 4 == 0, "elementwise: C=%d must be a multiple of 4", C);
-  EwArgs p{a, a_fp32, lda, b, b_fp32, ldb, out, out_fp32, ldo, rows, C, p_drop, seed};
+  EwArgs p{a, a_fp32, lda, b, b_fp32, ldb, out, out_fp32, ldo, rows, C, p_drop, seed, seed_dev};
   const int grid = grid_for(rows * (C / 4), 256);
   switch (op) {
     case 0: ew_kernel<0><<<grid, 256, 0, STREAM>>>(p); break;

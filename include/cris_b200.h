@@ -166,9 +166,10 @@ int cris_stem_conv1_wgrad(const float* img, const void* dz, int64_t lddz, float*
 /* ---- token ops (softmax/dropout inside MHA clip.py:119-139,255-260, layers.py:235,240-243; nn.Embedding
  *      clip.py:440-443; EOT gather clip.py:451-452; residual dropout layers.py:237,245,249; QuickGELU clip.py:234-236) */
 int cris_softmax_fwd(const void* S, void* P, void* Pd, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk,
-                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, void* stream);
+                     int heads, const int64_t* kpm_word, int causal, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* stream);
 int cris_softmax_bwd(const void* P, void* dP, int64_t ld, int64_t batch_stride, int nb, int Lq, int Lk, float p_drop,
-                     uint64_t seed, void* stream);
+                     uint64_t seed, const uint64_t* seed_dev, void* stream);
 int cris_embed_fwd(const int64_t* word, const float* table, const float* pos, float* x, int B, int L, int C,
                    void* stream);
 int cris_embed_bwd(const int64_t* word, const float* dx, float* dtable, float* dpos, int B, int L, int C,
@@ -177,9 +178,12 @@ int cris_eot_gather(const int64_t* word, const void* x, int x_fp32, int64_t ldx,
                     int C, void* stream);
 int cris_eot_scatter(const int64_t* word, const void* dout, int d_fp32, int64_t ldd, void* dx, int dx_fp32,
                      int64_t lddx, int B, int L, int C, void* stream);
-/* op 0: a(+b)  1: a+dropout(b)  2: dropout(a)  3: quickgelu(a)  4: b*quickgelu'(a)  5: (a>0)?b:0 */
+/* op 0: a(+b)  1: a+dropout(b)  2: dropout(a)  3: quickgelu(a)  4: b*quickgelu'(a)  5: (a>0)?b:0
+ * dropout masks are a pure function of (seed + *seed_dev, element index): seed_dev (device, may be NULL) lets a
+ * captured CUDA graph draw fresh masks on every replay. */
 int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void* b, int b_fp32, int64_t ldb, void* out,
-                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, void* stream);
+                     int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* stream);
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream);
 int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
 int cris_batch_reduce(const void* in, int in_fp32, int64_t ldin, float* out, int64_t ldo, int B, int T, int C,

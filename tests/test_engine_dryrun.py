@@ -54,6 +54,7 @@ def test_engine_host_logic(monkeypatch, training):
     model.train(training)
     img, word, mask = synth.make_inputs(2, 0, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
     e = model._get_engine()
+    e.use_graphs = False  # CUDA-graph capture needs a GPU; the eager path issues the same launches
     if not training:
         pred = e.run(img, word, None)
         assert pred.shape == (2, 1, 32, 32)
