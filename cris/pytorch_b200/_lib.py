@@ -94,6 +94,8 @@ def lib():
         L.cris_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
         L.cris_gemm.restype = C.c_int
         L.cris_set_gemm_impl.argtypes = [C.c_int]
+        L.cris_add_launch_count.argtypes = [C.c_uint64]
+        L.cris_add_launch_count.restype = None
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_T[ch] for ch in sig]
@@ -108,7 +110,7 @@ def lib():
 def exported_symbols():
     """Every entry point include/cris_b200.h declares (used by the CPU 'library loads' test)."""
     return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
-            "cris_launch_count", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
+            "cris_launch_count", "cris_add_launch_count", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

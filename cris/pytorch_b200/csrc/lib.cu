@@ -29,6 +29,7 @@ int cris_gemm_args_size(void) { return (int)sizeof(cris_gemm_args); }
 int cris_gemm_args_last_offset(void) { return (int)offsetof(cris_gemm_args, d_col_stride); }
 
 uint64_t cris_launch_count(void) { return cris::g_launches.load(); }
+void cris_add_launch_count(uint64_t n) { cris::g_launches.fetch_add(n); }
 
 int cris_device_check(void) {
   int dev = 0;

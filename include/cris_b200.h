@@ -35,6 +35,7 @@ int  cris_device_check(void);               /* 0 iff current device is sm_100 (B
 void cris_set_gemm_impl(int impl);
 int  cris_get_gemm_impl(void);
 uint64_t cris_launch_count(void);           /* kernels launched by this library so far    */
+void cris_add_launch_count(uint64_t n);     /* a replayed CUDA graph adds the launches it contains */
 
 /* ---- the GEMM / implicit-GEMM-conv core --------------------------------------------- */
 enum { CRIS_ACT_NONE = 0, CRIS_ACT_RELU = 1, CRIS_ACT_QUICKGELU = 2 };

@@ -31,6 +31,7 @@ def _mk_run(params=None, buffers=None, training=True, p_drop=0.0):
     r.Bf = {k: v.cuda() for k, v in (buffers or {}).items()}
     r.p_drop = p_drop
     r.seed_base, r.n_seed = 1234567, 0
+    r.seed_dev = None
     r.world, r.sync_bn = 1, False
     return r
 

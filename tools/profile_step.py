@@ -15,6 +15,7 @@ from oracle import synth  # noqa: E402
 
 
 def main():
+    os.environ.setdefault("CRIS_B200_GRAPHS", "0")  # per-kernel launch list: eager launches
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     arch = sys.argv[2] if len(sys.argv) > 2 else "r50"
     dev = torch.device("cuda", 0)
