@@ -82,7 +82,7 @@ __global__ void gemm_ref_kernel(const RefArgs r) {
   }
 }
 
-// partials[m_tile][2][N] from the stored D values (rows of a 128-row tile)
+// partials[m_tile % 64][2][N] (+)= column sums of the stored D values of a 128-row tile
 __global__ void gemm_ref_colstats(const cris_gemm_args a) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int mt = blockIdx.y;
@@ -97,8 +97,8 @@ __global__ void gemm_ref_colstats(const cris_gemm_args a) {
     s0 += x;
     s1 += x * x;
   }
-  a.colstats[(size_t)mt * 2 * a.N + n] = s0;
-  a.colstats[(size_t)mt * 2 * a.N + a.N + n] = s1;
+  atomicAdd(a.colstats + (size_t)(mt & 63) * 2 * a.N + n, s0);
+  atomicAdd(a.colstats + (size_t)(mt & 63) * 2 * a.N + a.N + n, s1);
 }
 
 int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream) {

@@ -2,12 +2,12 @@
 //
 //   D[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k]        bf16 x bf16 -> fp32 (TMEM)
 //
-// One CTA = one 128 x BN output tile.  Warp roles (192 threads):
+// Persistent: one CTA per SM walks 128 x BN output tiles (BN = 32..256).  Warp roles (192 threads):
 //   warps 0-3 : epilogue  (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
-//   warp  4   : TMA producer (cp.async.bulk.tensor into a STAGES-deep smem ring, mbarrier tx)
+//   warp  4   : TMA producer (cp.async.bulk.tensor into a STAGES-deep ~196 KB smem ring, mbarrier tx)
 //   warp  5   : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees slots)
-// Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's main loop.
+// The fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile j runs while
+// the MMAs of tile j+1 are issued, and the smem ring never drains between tiles.
 //
 // 3x3 convolution is an implicit GEMM over the zero-bordered ("padded NHWC") row matrix: tap
 // (dy,dx) is the same A matrix shifted by dy*(W+2)+dx rows, so a conv is 9 x (K/BK) k-blocks
@@ -52,10 +52,11 @@ struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = 98304 / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;   // one persistent CTA per SM
+  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;               // one accumulator buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                   // double-buffered accumulator
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -64,45 +65,62 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+struct TileCoord {
+  int n0, m0, split, ztap, b_in, b_out, kb_begin, kb_cnt, total_iters;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKArgs& p, int tile, int tiles_n, int tiles_m, int BNv) {
+  TileCoord t;
+  const int nt = tile % tiles_n;
+  int rest = tile / tiles_n;
+  const int mt = rest % tiles_m;
+  int z = rest / tiles_m;
+  t.n0 = nt * BNv;
+  t.m0 = mt * BM;
+  t.split = z % p.splits;
+  z /= p.splits;
+  t.ztap = z % p.taps_z;
+  const int batch = z / p.taps_z;
+  t.b_in = batch % p.batch_inner;
+  t.b_out = batch / p.batch_inner;
+  const int kb_per_split = (p.nkb + p.splits - 1) / p.splits;
+  t.kb_begin = t.split * kb_per_split;
+  const int kb_end = min(p.nkb, t.kb_begin + kb_per_split);
+  t.kb_cnt = max(0, kb_end - t.kb_begin);
+  t.total_iters = ((p.tap_mode == CRIS_TAP_ACCUM) ? p.taps : 1) * t.kb_cnt;
+  return t;
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (n fastest, so CTAs running
+// together share A rows in L2).  The smem ring keeps rolling across tiles; the TMEM accumulator is double
+// buffered so the epilogue of tile j overlaps the MMAs of tile j+1.
 template <int BN, int BK, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ GemmKArgs p) {
+                   const __grid_constant__ GemmKArgs p, int tiles_n, int tiles_m, int total_tiles) {
   using Cfg = TileCfg<BN, BK>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   __shared__ float s_stats[4][2][BN];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  int z = blockIdx.z;
-  const int split = z % p.splits;
-  z /= p.splits;
-  const int ztap = z % p.taps_z;
-  const int batch = z / p.taps_z;
-  const int b_in = batch % p.batch_inner, b_out = batch / p.batch_inner;
-
-  // k-block schedule of this CTA
-  const int kb_per_split = (p.nkb + p.splits - 1) / p.splits;
-  const int kb_begin = split * kb_per_split;
-  const int kb_end = min(p.nkb, kb_begin + kb_per_split);
-  const int kb_cnt = max(0, kb_end - kb_begin);
-  const int n_taps_loop = (p.tap_mode == CRIS_TAP_ACCUM) ? p.taps : 1;
-  const int total_iters = n_taps_loop * kb_cnt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -118,38 +136,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        const int t = (p.tap_mode == CRIS_TAP_ACCUM) ? (it / kb_cnt) : ztap;
-        const int kb = kb_begin + (it % kb_cnt);
-        const int k = kb * BK;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
-        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
-        const int a_row_off = (p.tap_mode == CRIS_TAP_ACCUM) ? p.tap_off[t] : 0;
-        int b_k_off = 0, b_n_off = 0;
-        if (p.tap_mode == CRIS_TAP_ACCUM) {
-          b_k_off = t * p.b_tap_k;
-          b_n_off = t * p.b_tap_n;
-        } else if (p.tap_mode == CRIS_TAP_WGRAD) {
-          b_k_off = p.tap_off[t];
-        }
-        if constexpr (!A_MN) {
-          ptx::tma_load_4d(sa, &tmA, &full_bar[s], k, m0 + a_row_off, b_in, b_out);
-        } else {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
+        for (int i = 0; i < tc.total_iters; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          const int t = (p.tap_mode == CRIS_TAP_ACCUM) ? (i / tc.kb_cnt) : tc.ztap;
+          const int k = (tc.kb_begin + (i % tc.kb_cnt)) * BK;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int a_row_off = (p.tap_mode == CRIS_TAP_ACCUM) ? p.tap_off[t] : 0;
+          int b_k_off = 0, b_n_off = 0;
+          if (p.tap_mode == CRIS_TAP_ACCUM) {
+            b_k_off = t * p.b_tap_k;
+            b_n_off = t * p.b_tap_n;
+          } else if (p.tap_mode == CRIS_TAP_WGRAD) {
+            b_k_off = p.tap_off[t];
+          }
+          if constexpr (!A_MN) {
+            ptx::tma_load_4d(sa, &tmA, &full_bar[s], k, tc.m0 + a_row_off, tc.b_in, tc.b_out);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i)
-            ptx::tma_load_4d(sa + i * (BK * 128), &tmA, &full_bar[s], m0 + 64 * i, k, b_in, b_out);
-        }
-        if constexpr (!B_MN) {
-          ptx::tma_load_4d(sb, &tmB, &full_bar[s], k + b_k_off, n0 + b_n_off, b_in, b_out);
-        } else {
+            for (int q = 0; q < BM / 64; ++q)
+              ptx::tma_load_4d(sa + q * (BK * 128), &tmA, &full_bar[s], tc.m0 + 64 * q, k, tc.b_in, tc.b_out);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_4d(sb, &tmB, &full_bar[s], k + b_k_off, tc.n0 + b_n_off, tc.b_in, tc.b_out);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            ptx::tma_load_4d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + b_n_off + 64 * j, k + b_k_off,
-                             b_in, b_out);
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_4d(sb + j * (BK * 128), &tmB, &full_bar[s], tc.n0 + b_n_off + 64 * j, k + b_k_off,
+                               tc.b_in, tc.b_out);
+          }
         }
       }
     }
@@ -159,192 +180,219 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint64_t k_layout = (BK == 64) ? ptx::kLayoutSW128 : ptx::kLayoutSW64;
       constexpr uint32_t k_sbo = (BK == 64) ? 1024u : 512u;
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        ptx::mbar_wait(&full_bar[s], ph, 200 + s);
+      int it = 0, acc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
+        if (tc.total_iters == 0) continue;
+        const int buf = acc & 1;
+        ptx::mbar_wait(&tmem_empty[buf], (((uint32_t)acc >> 1) & 1u) ^ 1u, 400 + buf);  // epilogue drained it
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        const uint64_t adesc = A_MN ? ptx::make_smem_desc(sa, BK * 128, 1024, ptx::kLayoutSW128)
-                                    : ptx::make_smem_desc(sa, 16, k_sbo, k_layout);
-        const uint64_t bdesc = B_MN ? ptx::make_smem_desc(sb, BK * 128, 1024, ptx::kLayoutSW128)
-                                    : ptx::make_smem_desc(sb, 16, k_sbo, k_layout);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
+        for (int i = 0; i < tc.total_iters; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          ptx::mbar_wait(&full_bar[s], ph, 200 + s);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = A_MN ? ptx::make_smem_desc(sa, BK * 128, 1024, ptx::kLayoutSW128)
+                                      : ptx::make_smem_desc(sa, 16, k_sbo, k_layout);
+          const uint64_t bdesc = B_MN ? ptx::make_smem_desc(sb, BK * 128, 1024, ptx::kLayoutSW128)
+                                      : ptx::make_smem_desc(sb, 16, k_sbo, k_layout);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // advance 16 k-elements: K-major = 32 B inside the swizzled row; MN-major = 16 rows of 128 B
-          const uint64_t a_adv = (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4);
-          const uint64_t b_adv = (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4);
-          ptx::umma_bf16(tmem_base, adesc + a_adv, bdesc + b_adv, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 k-elements: K-major = 32 B inside the swizzled row; MN-major = 16 rows of 128 B
+            const uint64_t a_adv = (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4);
+            const uint64_t b_adv = (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4);
+            ptx::umma_bf16(tacc, adesc + a_adv, bdesc + b_adv, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        ptx::umma_commit(&tmem_full[buf]);  // accumulator of this tile complete
+        ++acc;
       }
-      ptx::umma_commit(tmem_full);  // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 0-3) =====================
-    const long long row = (long long)m0 + warp * 32 + lane;
-    const bool row_in = row < p.M;
-    const bool row_valid = row_in && interior_row(row, p.mask_hp, p.mask_wp);
-    const int dcol0 = n0 + ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
     uint8_t* Dbase = reinterpret_cast<uint8_t*>(p.D);
-    const long long drow = (long long)b_out * p.strideD + (long long)b_in * p.strideD2 + row * p.ldd;
-    const long long rrow = (long long)b_out * p.strideR + (long long)b_in * p.strideR2 + row * p.ldr;
-    if (total_iters > 0) {
-      ptx::mbar_wait(tmem_full, 0, 300);
-      ptx::tc_fence_after();
-    }
+    int acc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
+      const int n0 = tc.n0, ztap = tc.ztap;
+      const long long row = (long long)tc.m0 + warp * 32 + lane;
+      const bool row_in = row < p.M;
+      const bool row_valid = row_in && interior_row(row, p.mask_hp, p.mask_wp);
+      const int dcol0 = n0 + ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
+      const long long drow = (long long)tc.b_out * p.strideD + (long long)tc.b_in * p.strideD2 + row * p.ldd;
+      const long long rrow = (long long)tc.b_out * p.strideR + (long long)tc.b_in * p.strideR2 + row * p.ldr;
+      const bool has_acc = tc.total_iters > 0;
+      const int buf = acc & 1;
+      if (has_acc) {
+        ptx::mbar_wait(&tmem_full[buf], ((uint32_t)acc >> 1) & 1u, 300 + buf);
+        ptx::tc_fence_after();
+      }
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      if (total_iters > 0) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
-        ptx::tmem_ld_wait();
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        if (has_acc) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      const int ncol0 = n0 + c * 32;  // logical column (bias / N bound)
-      if (ncol0 >= p.N) {
-        if (p.colstats != nullptr) {
-          s_stats[warp][0][c * 32 + lane] = 0.f;
-          s_stats[warp][1][c * 32 + lane] = 0.f;
-        }
-        continue;
-      }
-      if (p.bias != nullptr) {
-        const float* bp = p.bias + ncol0;
-        if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(bp + j));
-            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ncol0 + j < p.N) v[j] += __ldg(bp + j);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-      }
-      if (p.act != CRIS_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-      }
-      if (p.resid != nullptr && row_in) {
-        if (p.resid_fp32) {
-          const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
-          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+        if (c == BN / 32 - 1 && has_acc) {
+          // all TMEM reads of this tile are done: hand the accumulator buffer back to the MMA warp
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        }
+        const int ncol0 = n0 + c * 32;  // logical column (bias / N bound)
+        if (ncol0 >= p.N) {
+          if (p.colstats != nullptr) {
+            s_stats[warp][0][c * 32 + lane] = 0.f;
+            s_stats[warp][1][c * 32 + lane] = 0.f;
+          }
+          continue;
+        }
+        if (p.bias != nullptr) {
+          const float* bp = p.bias + ncol0;
+          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 q = *reinterpret_cast<const float4*>(rp + j);
+              const float4 q = __ldg(reinterpret_cast<const float4*>(bp + j));
               v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) v[j] += rp[j];
-          }
-        } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
-          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-              const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c2 = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-              v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
-              v[j + 4] += c2.x; v[j + 5] += c2.y; v[j + 6] += d.x; v[j + 7] += d.y;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
+              if (ncol0 + j < p.N) v[j] += __ldg(bp + j);
           }
         }
-      }
-      if (!row_valid) {
+        if (p.act != CRIS_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      // ---- store ----
-      if (row_in) {
-        if (p.d_fp32) {
-          float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
-          if (p.accumulate) {
-            float* ap = reinterpret_cast<float*>(Dbase) + drow +
-                        ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        if (p.resid != nullptr && row_in) {
+          if (p.resid_fp32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
-          } else if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+              for (int j = 0; j < 32; j += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) dp[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(Dbase) + drow + dcol0 + c * 32;
-          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]);
-              q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(dp + j) = q;
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) v[j] += rp[j];
             }
           } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) dp[j] = f2bf(v[j]);
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                const float2 e0 = unpack_bf16x2(q.x), e1 = unpack_bf16x2(q.y), e2 = unpack_bf16x2(q.z),
+                             e3 = unpack_bf16x2(q.w);
+                v[j] += e0.x; v[j + 1] += e0.y; v[j + 2] += e1.x; v[j + 3] += e1.y;
+                v[j + 4] += e2.x; v[j + 5] += e2.y; v[j + 6] += e3.x; v[j + 7] += e3.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
+            }
           }
         }
+        if (!row_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        // ---- store ----
+        if (row_in) {
+          if (p.d_fp32) {
+            float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
+            if (p.accumulate) {
+              float* ap = reinterpret_cast<float*>(Dbase) + drow +
+                          ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
+            } else if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) dp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(Dbase) + drow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 q;
+                q.x = pack_bf16x2(v[j], v[j + 1]);
+                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(dp + j) = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) dp[j] = f2bf(v[j]);
+            }
+          }
+        }
+        // ---- per-column batch statistics of the STORED (rounded) values ----
+        if (p.colstats != nullptr) {
+          float a[32], q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = p.d_fp32 ? v[j] : bf2f(f2bf(v[j]));
+            if (!(ncol0 + j < p.N)) x = 0.f;
+            a[j] = x;
+            q[j] = x * x;
+          }
+          // transposing butterfly: after the 5 steps lane L holds the 32-lane total of column L
+#pragma unroll
+          for (int s = 16; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+              const float send_a = up ? a[i] : a[i + s];
+              const float keep_a = up ? a[i + s] : a[i];
+              a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
+              const float send_q = up ? q[i] : q[i + s];
+              const float keep_q = up ? q[i + s] : q[i];
+              q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
+            }
+          }
+          s_stats[warp][0][c * 32 + lane] = a[0];
+          s_stats[warp][1][c * 32 + lane] = q[0];
+        }
       }
-      // ---- per-column batch statistics of the STORED (rounded) values ----
       if (p.colstats != nullptr) {
-        float a[32], q[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = p.d_fp32 ? v[j] : bf2f(f2bf(v[j]));
-          if (!(ncol0 + j < p.N)) x = 0.f;
-          a[j] = x;
-          q[j] = x * x;
-        }
-        // transposing butterfly: after the 5 steps lane L holds the 32-lane total of column L
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-          const bool up = (lane & s) != 0;
-#pragma unroll
-          for (int i = 0; i < s; ++i) {
-            const float send_a = up ? a[i] : a[i + s];
-            const float keep_a = up ? a[i + s] : a[i];
-            a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
-            const float send_q = up ? q[i] : q[i + s];
-            const float keep_q = up ? q[i + s] : q[i];
-            q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = threadIdx.x; j < BN; j += 128) {
+          if (n0 + j < p.N) {
+            const float s0 = s_stats[0][0][j] + s_stats[1][0][j] + s_stats[2][0][j] + s_stats[3][0][j];
+            const float s1 = s_stats[0][1][j] + s_stats[1][1][j] + s_stats[2][1][j] + s_stats[3][1][j];
+            // 64 partial rows (m_tile % 64): spreads the atomics, keeps the follow-up reduction tiny
+            float* dst = p.colstats + (size_t)((tc.m0 / BM) & 63) * 2 * p.N;
+            atomicAdd(dst + n0 + j, s0);
+            atomicAdd(dst + p.N + n0 + j, s1);
           }
         }
-        s_stats[warp][0][c * 32 + lane] = a[0];
-        s_stats[warp][1][c * 32 + lane] = q[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats is reused by the next tile
       }
-    }
-    if (p.colstats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int j = threadIdx.x; j < BN; j += 128) {
-        if (n0 + j < p.N) {
-          const float s0 = s_stats[0][0][j] + s_stats[1][0][j] + s_stats[2][0][j] + s_stats[3][0][j];
-          const float s1 = s_stats[0][1][j] + s_stats[1][1][j] + s_stats[2][1][j] + s_stats[3][1][j];
-          float* dst = p.colstats + (size_t)blockIdx.y * 2 * p.N;
-          dst[n0 + j] = s0;
-          dst[p.N + n0 + j] = s1;
-        }
-      }
+      if (has_acc) ++acc;
     }
   }
 
@@ -401,6 +449,31 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long inner_extent, 
   return 0;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// tile width: the widest BN whose tile count still fills the machine (wide tiles halve the A re-reads)
+static int pick_bn(const cris_gemm_args* a, int max_bn) {
+  const long long z = (long long)a->batch * (a->tap_mode == CRIS_TAP_WGRAD ? a->taps : 1) * a->splits;
+  const long long tm = (a->M + BM - 1) / BM;
+  for (int bn = max_bn; bn > 64; bn >>= 1) {
+    if (a->N < bn / 2 + 1) continue;
+    const long long tiles = tm * ((a->N + bn - 1) / bn) * z;
+    if (tiles >= num_sms() || bn == 128) {
+      if (a->N > bn / 2) return bn;
+    }
+  }
+  return a->N <= 32 ? 32 : 64;
+}
+
 template <int BN, int BK, bool A_MN, bool B_MN>
 static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
   using Cfg = TileCfg<BN, BK>;
@@ -437,8 +510,11 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
     CRIS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM, a->batch * kk.taps_z * kk.splits);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kk);
+  const int tiles_n = (a->N + BN - 1) / BN, tiles_m = (a->M + BM - 1) / BM;
+  const long long total = (long long)tiles_n * tiles_m * a->batch * kk.taps_z * kk.splits;
+  CRIS_CHECK_ARG(total < (1ll << 31), "GEMM has too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kk, tiles_n, tiles_m, (int)total);
   CRIS_LAUNCH_OK();
   return 0;
 }
@@ -485,18 +561,22 @@ int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
     if (a->N <= 64) return launch_tc<64, 32, false, false>(a, k, stream);
     return launch_tc<128, 32, false, false>(a, k, stream);
   }
+  const int bn = pick_bn(a, 256);
   if (!amn && !bmn) {
-    if (a->N <= 32) return launch_tc<32, 64, false, false>(a, k, stream);
-    if (a->N <= 64) return launch_tc<64, 64, false, false>(a, k, stream);
-    return launch_tc<128, 64, false, false>(a, k, stream);
+    if (bn == 32) return launch_tc<32, 64, false, false>(a, k, stream);
+    if (bn == 64) return launch_tc<64, 64, false, false>(a, k, stream);
+    if (bn == 128) return launch_tc<128, 64, false, false>(a, k, stream);
+    return launch_tc<256, 64, false, false>(a, k, stream);
   }
   if (!amn && bmn) {
-    if (a->N <= 64) return launch_tc<64, 64, false, true>(a, k, stream);
-    return launch_tc<128, 64, false, true>(a, k, stream);
+    if (bn <= 64) return launch_tc<64, 64, false, true>(a, k, stream);
+    if (bn == 128) return launch_tc<128, 64, false, true>(a, k, stream);
+    return launch_tc<256, 64, false, true>(a, k, stream);
   }
   if (amn && bmn) {
-    if (a->N <= 64) return launch_tc<64, 64, true, true>(a, k, stream);
-    return launch_tc<128, 64, true, true>(a, k, stream);
+    if (bn <= 64) return launch_tc<64, 64, true, true>(a, k, stream);
+    if (bn == 128) return launch_tc<128, 64, true, true>(a, k, stream);
+    return launch_tc<256, 64, true, true>(a, k, stream);
   }
   set_error("GEMM operand majorness a_mn=1,b_mn=0 is not instantiated");
   return -1;

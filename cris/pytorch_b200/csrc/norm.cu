@@ -44,39 +44,48 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
       ld8f(p.rstd + c, rs);
     }
     if (tr < R) {
-      for (long long r = r0 + tr; r < r1; r += R) {
-        if (MODE != 3 && !interior_row(r, p.hp, p.wp)) continue;
-        float a[8];
-        ld8x(p.a, r * p.lda + c, p.a_fp32, a);
-        if (MODE == 0) {
+      // U rows per trip: all loads of a trip are issued before any is consumed (memory-level parallelism)
+      constexpr int U = (MODE == 1) ? 3 : 4;
+      for (long long rb = r0 + tr; rb < r1; rb += (long long)R * U) {
+        float a[U][8], xv[U][8], yv[U][8];
+        bool ok[U];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * a[i]; }
-        } else if (MODE == 2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s0[i] += a[i];
-        } else if (MODE == 1) {
-          float xv[8];
-          ld8x(p.x, r * p.ldx + c, p.x_fp32, xv);
-          if (p.relu) {
-            float yv[8];
-            ld8(reinterpret_cast<const __nv_bfloat16*>(p.y) + r * p.ldy + c, yv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (!(yv[i] > 0.f)) a[i] = 0.f;
+        for (int u = 0; u < U; ++u) {
+          const long long r = rb + (long long)u * R;
+          ok[u] = r < r1 && (MODE == 3 || interior_row(r, p.hp, p.wp));
+          if (ok[u]) {
+            ld8x(p.a, r * p.lda + c, p.a_fp32, a[u]);
+            if (MODE == 1 || MODE == 3) ld8x(p.x, r * p.ldx + c, p.x_fp32, xv[u]);
+            if (MODE == 1 && p.relu) ld8(reinterpret_cast<const __nv_bfloat16*>(p.y) + r * p.ldy + c, yv[u]);
+            if (MODE == 3 && p.a2 != nullptr) ld8(reinterpret_cast<const __nv_bfloat16*>(p.a2) + r * p.lda2 + c, yv[u]);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * (xv[i] - mu[i]) * rs[i]; }
-        } else {
-          float xv[8];
-          ld8x(p.x, r * p.ldx + c, p.x_fp32, xv);
-          if (p.a2 != nullptr) {
-            float b[8];
-            ld8(reinterpret_cast<const __nv_bfloat16*>(p.a2) + r * p.lda2 + c, b);
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          const long long r = rb + (long long)u * R;
+          if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] += b[i];
+            for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] += a[u][i] * a[u][i]; }
+          } else if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s0[i] += a[u][i];
+          } else if (MODE == 1) {
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) if (!(yv[u][i] > 0.f)) a[u][i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] += a[u][i] * (xv[u][i] - mu[i]) * rs[i]; }
+          } else {
+            if (p.a2 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[u][i] += yv[u][i];
+            }
+            const float m = p.mean[r], sd = p.rstd[r];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] += a[u][i] * (xv[u][i] - m) * sd; }
           }
-          const float m = p.mean[r], s = p.rstd[r];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { s0[i] += a[i]; s1[i] += a[i] * (xv[i] - m) * s; }
         }
       }
     }

@@ -269,6 +269,9 @@ class GraphedStep:
                 self.n_fwd, self.n_bwd = n1 - n0, _lib.launch_count() - n1  # kernels inside each graph
                 _lib.lib().cris_add_launch_count(-(self.n_fwd + self.n_bwd) & ((1 << 64) - 1))  # capture != launch
                 self.run = r  # keeps every captured buffer referenced
+            import gc
+            gc.collect()
+            gc.freeze()  # the captured pass holds ~10^5 long-lived objects: keep them out of later GC passes
         finally:
             engine.packed.force = False
 
@@ -531,8 +534,8 @@ class Run:
         cin = w_cols if cin is None else cin
         cin_pad = _r8(w_cols)
         z = self.new(x.rows, cout, False, x.geom)
-        n_tiles = (x.rows + 127) // 128
-        part = self.f32(n_tiles * 2 * cout) if stats else None
+        n_tiles = min(64, (x.rows + 127) // 128)
+        part = self.f32(n_tiles * 2 * cout, zero=True) if stats else None
         bias = self.P[bias_name].data_ptr() if bias_name else None
         offs = self.taps_of(x.geom) if k == 3 else None
         probe = self.e.probe_name == wname
@@ -630,8 +633,8 @@ class Run:
             wv = wp.rows_slice(r0, r1)
         bias_ptr = (self.P[bname].data_ptr() + 4 * r0) if bname else None
         y = out if out is not None else self.new(x.rows, n_out, out_fp32, None, ld=_r8(n_out))
-        n_tiles = (x.rows + 127) // 128
-        part = self.f32(n_tiles * 2 * n_out) if stats else None
+        n_tiles = min(64, (x.rows + 127) // 128)
+        part = self.f32(n_tiles * 2 * n_out, zero=True) if stats else None
         self.gemm(x, wv, y, x.rows, n_out, n_in, b_mn=1 if transposed_weight else 0, bias=bias_ptr, act=act,
                   colstats=part.data_ptr() if stats else None, b_rows=n_in if transposed_weight else 0)
 
@@ -1157,7 +1160,7 @@ class Run:
              g.data_ptr(), dl.data_ptr(), dxf.ptr, dxf.ld, dt.ptr, dt.ld, B, Ho, Wo, C)
         for fn in reversed(self.tape):
             fn()
-        self.tape = []
+        self.tape = []  # closures <-> Run form reference cycles; drop them so buffers are freed promptly
         out = []
         for k in names:
             out.append(self.pgrad.get(k))

@@ -62,8 +62,8 @@ enum { CRIS_TAP_NONE = 0, CRIS_TAP_ACCUM = 1, CRIS_TAP_WGRAD = 2 };
  * splits > 1 divides the K loop over `splits` CTAs that atomically add into fp32 D
  * (requires d_fp32 = 1, accumulate = 1; D pre-zeroed by the caller unless accumulating).
  * Epilogue order: acc*alpha -> +bias[n] -> act -> +resid -> row mask -> store / atomic add
- *   -> optional per-column (sum, sumsq) partials of the stored values into
- *      colstats[m_tile][2][N] (fp32), m_tile = m/128 — the BatchNorm batch statistics.
+ *   -> optional per-column (sum, sumsq) partials of the stored values atomically added into
+ *      colstats[(m/128) % 64][2][N] (fp32, zeroed by the caller) — the BatchNorm batch statistics.
  * Row mask: if mask_wp > 0, row r is a padded-NHWC pixel (h,w) = ((r % (mask_hp*mask_wp)) / mask_wp,
  *   r % mask_wp); border rows (h==0, h==hp-1, w==0, w==wp-1) are written as zero.
  */
@@ -84,7 +84,7 @@ typedef struct cris_gemm_args {
   int32_t act;
   const void* resid; int64_t ldr; int64_t strideR; int32_t resid_fp32;
   int32_t mask_hp, mask_wp;
-  float*  colstats;          /* [ceil(M/128)][2][N] fp32 or NULL */
+  float*  colstats;          /* [min(64, ceil(M/128))][2][N] fp32, pre-zeroed, or NULL */
   int32_t a_rows, b_rows;    /* physical row extents of A/B for OOB zero fill (0 = derive) */
   /* two-level batch: batch index z -> (outer = z / batch_inner, inner = z % batch_inner); the outer level
    * uses strideA/B/D/R above, the inner level the strides below (attention heads: inner = head, stride 64) */

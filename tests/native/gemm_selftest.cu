@@ -62,6 +62,12 @@ static std::vector<Case> make_cases() {
   add("nt_K32_N64", 1000, 64, 32, 1, 0, 0);
   add("nt_batched_676x676x64", 676, 676, 64, 5, 0, 0);
   add("nt_batched_17x17x64", 17, 17, 64, 7, 0, 0)->cpu_check = 1;
+  // persistent scheduling: more tiles than SMs (several tiles per CTA, both TMEM accumulator buffers in flight)
+  add("nt_many_tiles_20000x512x256", 20000, 512, 256, 1, 0, 0);
+  { auto x = add("nt_many_tiles_bias_relu_resid", 30000, 192, 64, 1, 0, 0); x->bias = 1; x->act = 1; x->resid = 1; }
+  { auto x = add("conv_fwd_many_tiles_stats", 40 * 30 * 30, 256, 128, 1, 0, 0); x->tap_mode = 1; x->taps = 9; x->hp = 30; x->wp = 30; x->mask = 1; x->colstats = 1; }
+  { auto x = add("conv_wgrad_many_tiles", 256, 384, 40 * 30 * 30, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 30; x->wp = 30; x->d_fp32 = 1; x->accumulate = 1; x->splits = 6; }
+  add("nt_batched_many_676x676x64", 676, 676, 64, 40, 0, 0);
   // two-level batch: per-head slices of packed [B, L, heads*64] projections (attention)
   { auto x = add("heads_qk_100x100x64", 100, 100, 64, 8, 0, 0); x->heads = 4; x->cpu_check = 1; x->alpha = 0.125f; }
   { auto x = add("heads_pv_100x64x100", 100, 64, 100, 8, 0, 1); x->heads = 4; x->cpu_check = 1; }
