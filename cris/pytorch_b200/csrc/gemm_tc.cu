@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   __shared__ float s_stats[4][2][BN];
-  __shared__ __align__(16) uint8_t s_stage[4][32 * 144];  // per-warp 32 x 128 B (+16 B pad) transpose buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -228,11 +227,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long rrow = (long long)tc.b_out * p.strideR + (long long)tc.b_in * p.strideR2 + row * p.ldr;
       const bool has_acc = tc.total_iters > 0;
       const int buf = acc & 1;
-      // warp-cooperative (coalesced) global access: lane -> (row group, 16-byte piece) of a 32-row x 32-col chunk
-      const long long wrow0 = (long long)tc.m0 + warp * 32;
-      const long long dwarp = (long long)tc.b_out * p.strideD + (long long)tc.b_in * p.strideD2 + wrow0 * p.ldd;
-      const long long rwarp = (long long)tc.b_out * p.strideR + (long long)tc.b_in * p.strideR2 + wrow0 * p.ldr;
-      uint8_t* stg = s_stage[warp];
       if (has_acc) {
         ptx::mbar_wait(&tmem_full[buf], ((uint32_t)acc >> 1) & 1u, 300 + buf);
         ptx::tc_fence_after();
@@ -282,51 +276,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
         }
-        if (p.resid != nullptr) {
-          const int esz = p.resid_fp32 ? 4 : 2;
-          const uint8_t* rbase = reinterpret_cast<const uint8_t*>(p.resid) + (rwarp + dcol0 + c * 32) * esz;
-          const bool vec_ok = (ncol0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(rbase) & 15) == 0) &&
-                              (((p.ldr * esz) & 15) == 0);
-          if (vec_ok) {
-            // coalesced: pieces of 16 B, (128 / esz... ) per row; 32 rows staged through smem
-            const int ppr = p.resid_fp32 ? 8 : 4;          // 16-byte pieces per row (128 B or 64 B)
-            const int rpi = 32 / ppr;                        // rows per warp instruction
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < ppr) {
-                const int rr = i * rpi + lane / ppr, piece = lane % ppr;
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (wrow0 + rr < p.M)
-                  q = *reinterpret_cast<const uint4*>(rbase + (long long)rr * p.ldr * esz + piece * 16);
-                *reinterpret_cast<uint4*>(stg + rr * 144 + piece * 16) = q;
-              }
-            }
-            __syncwarp();
-            if (p.resid_fp32) {
+        if (p.resid != nullptr && row_in) {
+          if (p.resid_fp32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(stg + lane * 144 + j * 4);
+                const float4 q = *reinterpret_cast<const float4*>(rp + j);
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
               }
             } else {
 #pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) v[j] += rp[j];
+            }
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 q = *reinterpret_cast<const uint4*>(stg + lane * 144 + j * 2);
+                const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
                 const float2 e0 = unpack_bf16x2(q.x), e1 = unpack_bf16x2(q.y), e2 = unpack_bf16x2(q.z),
                              e3 = unpack_bf16x2(q.w);
                 v[j] += e0.x; v[j + 1] += e0.y; v[j + 2] += e1.x; v[j + 3] += e1.y;
                 v[j + 4] += e2.x; v[j + 5] += e2.y; v[j + 6] += e3.x; v[j + 7] += e3.y;
               }
-            }
-            __syncwarp();
-          } else if (row_in) {
-            if (p.resid_fp32) {
-              const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) v[j] += rp[j];
             } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
@@ -338,26 +313,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         // ---- store ----
-        if (p.d_fp32 && p.accumulate) {
-          if (row_in) {
-            float* ap = reinterpret_cast<float*>(Dbase) + drow + ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
+        if (row_in) {
+          if (p.d_fp32) {
+            float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
+            if (p.accumulate) {
+              float* ap = reinterpret_cast<float*>(Dbase) + drow +
+                          ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
-          }
-        } else {
-          const int esz = p.d_fp32 ? 4 : 2;
-          uint8_t* dbase = Dbase + (dwarp + dcol0 + c * 32) * esz;
-          const bool vec_ok = (ncol0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) &&
-                              (((p.ldd * esz) & 15) == 0);
-          if (vec_ok) {
-            // registers (one row per lane) -> smem -> coalesced 16 B pieces: each warp store instruction covers
-            // whole 64 B / 128 B row segments instead of 32 scattered rows
-            if (p.d_fp32) {
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
+            } else if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(stg + lane * 144 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < p.N) dp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(Dbase) + drow + dcol0 + c * 32;
+            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 q;
@@ -365,30 +341,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 q.y = pack_bf16x2(v[j + 2], v[j + 3]);
                 q.z = pack_bf16x2(v[j + 4], v[j + 5]);
                 q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(stg + lane * 144 + j * 2) = q;
+                *reinterpret_cast<uint4*>(dp + j) = q;
               }
-            }
-            __syncwarp();
-            const int ppr = p.d_fp32 ? 8 : 4;
-            const int rpi = 32 / ppr;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < ppr) {
-                const int rr = i * rpi + lane / ppr, piece = lane % ppr;
-                if (wrow0 + rr < p.M)
-                  *reinterpret_cast<uint4*>(dbase + (long long)rr * p.ldd * esz + piece * 16) =
-                      *reinterpret_cast<const uint4*>(stg + rr * 144 + piece * 16);
-              }
-            }
-            __syncwarp();
-          } else if (row_in) {
-            if (p.d_fp32) {
-              float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) dp[j] = v[j];
             } else {
-              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(Dbase) + drow + dcol0 + c * 32;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (ncol0 + j < p.N) dp[j] = f2bf(v[j]);

@@ -158,6 +158,7 @@ class Engine:
         self.probe_events: List = []
         # whole-pass CUDA graphs (forward graph + backward graph per input shape): removes ~2000 host launches/step
         self.use_graphs = os.environ.get("CRIS_B200_GRAPHS", "1") != "0"
+        self.force_sync_bn = False  # tests: exercise the cross-rank BN exchange without SyncBatchNorm modules
         self.graphs: Dict[tuple, "GraphedStep"] = {}
         self._counter: Optional[torch.Tensor] = None
         _lib.lib()
@@ -322,8 +323,8 @@ class Run:
         self.n_seed = 0
         self.seed_dev = engine.step_counter(self.dev).data_ptr()
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        self.sync_bn = training and self.world > 1 and any(
-            isinstance(m, nn.SyncBatchNorm) for m in self.model.modules())
+        self.sync_bn = training and self.world > 1 and (engine.force_sync_bn or any(
+            isinstance(m, nn.SyncBatchNorm) for m in self.model.modules()))
 
     # ---- small helpers -------------------------------------------------------------------------
     def new(self, rows, C, fp32=False, geom=None, zero=False, ld=None) -> Mat:
