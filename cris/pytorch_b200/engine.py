@@ -189,7 +189,9 @@ class Engine:
                     continue
                 names.append(k)
                 params.append(p)
-            if self.use_graphs and self.debug_taps is None and self.probe_name is None:
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            graphs_ok = self.use_graphs and (not multi or os.environ.get("CRIS_B200_GRAPHS_DDP", "0") == "1")
+            if graphs_ok and self.debug_taps is None and self.probe_name is None:
                 key = (tuple(img.shape), tuple(word.shape), tuple(mask.shape), img.device.index, float(model.dropout_p))
                 gs = self.graphs.get(key)
                 if gs is None:
