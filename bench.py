@@ -279,7 +279,7 @@ def main():
                 "h2d_bytes_per_step": int(img_h.numel() * 4 + word_h.numel() * 8 + mask_h.numel() * 4),
                 "d2h_bytes_per_step": 12},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<128,64> implicit-GEMM conv3x3 proj.vis.3 fwd",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256,64,K-major,K-major> implicit-GEMM conv3x3 proj.vis.3 fwd (persistent tcgen05)",
                      "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                      "traffic": traffic, "peak_source": pk_src + " (burst, kernel timed alone by events)",
                      "kernel_ms": k_ms, "flop_per_launch": k_flop,
