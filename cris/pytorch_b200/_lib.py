@@ -110,7 +110,7 @@ def lib():
 def exported_symbols():
     """Every entry point include/cris_b200.h declares (used by the CPU 'library loads' test)."""
     return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
-            "cris_launch_count", "cris_add_launch_count", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
+            "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

@@ -73,9 +73,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // padded-NHWC row -> is it an interior pixel?
 __device__ __forceinline__ bool interior_row(long long r, int hp, int wp) {
   if (wp <= 0) return true;
-  int rr = (int)(r % ((long long)hp * wp));
-  int h = rr / wp, w = rr - h * wp;
-  return (h >= 1) && (h <= hp - 2) && (w >= 1) && (w <= wp - 2);
+  // row indices fit 32 bits in every use (B*(H+2)*(W+2) < 2^31): 32-bit division, not the 64-bit subroutine
+  const unsigned rr = (unsigned)r % (unsigned)(hp * wp);
+  const unsigned h = rr / (unsigned)wp, w = rr - h * (unsigned)wp;
+  return (h >= 1u) && (h <= (unsigned)(hp - 2)) && (w >= 1u) && (w <= (unsigned)(wp - 2));
 }
 
 }  // namespace cris

@@ -2,10 +2,10 @@
 //
 //   D[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k]        bf16 x bf16 -> fp32 (TMEM)
 //
-// Persistent: one CTA per SM walks 128 x BN output tiles (BN = 32..256).  Warp roles (192 threads):
-//   warps 0-3 : epilogue  (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
-//   warp  4   : TMA producer (cp.async.bulk.tensor into a STAGES-deep ~196 KB smem ring, mbarrier tx)
-//   warp  5   : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees slots)
+// Persistent: one CTA per SM walks 128 x BN output tiles (BN = 32..256).  Warp roles (320 threads):
+//   warps 0-7 : epilogue  (tcgen05.ld TMEM -> registers -> fused epilogue -> global), 2 per SM sub-partition
+//   warp  8   : TMA producer (cp.async.bulk.tensor into a STAGES-deep ~196 KB smem ring, mbarrier tx)
+//   warp  9   : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees slots)
 // The fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile j runs while
 // the MMAs of tile j+1 are issued, and the smem ring never drains between tiles.
 //
@@ -42,10 +42,14 @@ struct GemmKArgs {
   int mask_hp, mask_wp;
   float* colstats;
   int d_col_stride;
+  int tma_store;     // D is written with TMA tile stores (bf16/fp32, dense, 16 B aligned pitch)
+  unsigned flags;    // F_* bits
+  long long* trace;  // debug: clock64 stamps of CTA 0 / thread 0 (16 per tile), or null
 };
 
 constexpr int BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // 2 per SM sub-partition: a lone warp cannot hide ALU latency
+constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;  // + TMA producer warp + MMA issuer warp
 
 template <int BN, int BK>
 struct TileCfg {
@@ -63,6 +67,209 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == CRIS_ACT_RELU) return fmaxf(v, 0.f);
   if (act == CRIS_ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));
   return v;
+}
+
+
+// ---- epilogue of one 32-column chunk (one output row per lane) -------------------------------------------
+// The hot loop must stay compact and contiguous: with every option inlined behind runtime flags one chunk
+// iteration jumped across ~58 KB of SASS and was instruction-fetch bound (ncu: stall_no_inst /
+// branch_resolving, ~860 cycles per 100 executed instructions).  EPI specialises the common cases at compile
+// time; everything rare (partial / unaligned chunks, QuickGELU, fp32 residuals) takes the cold generic branch.
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_RESID = 2, EPI_ACCUM = 3 };
+// runtime option bits, evaluated on the HOST and kept in one ordinary register: testing kernel-parameter fields
+// inside the chunk loop costs a constant-bank load -> uniform predicate -> branch chain (~50-100 cycles each with
+// only two warps per scheduler to hide it; ncu: stall_short_sb on UISETP after LDCU)
+enum { F_BIAS = 1, F_RELU = 2, F_FAST = 4, F_TMA = 8, F_DFP32 = 16, F_STATS = 32, F_WGRAD = 64, F_ALPHA = 128 };
+
+struct ChunkCtx {
+  long long drow, rrow;  // element offsets of this lane's row in D / resid (batch offsets included)
+  int ncol0;             // logical first column of the chunk (bias index / N bound)
+  int dcol;              // first D column of the chunk (tap offset included)
+  int ztap;
+  bool row_in, row_valid;
+};
+
+// per-column (sum, sumsq) over the 32 lanes: transposing butterfly, lane L ends with column L
+__device__ __forceinline__ void chunk_colstats(const GemmKArgs& p, const float (&v)[32], int ncol0, int lane,
+                                               float* st0, float* st1) {
+  float a[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = p.d_fp32 ? v[j] : bf2f(f2bf(v[j]));
+    if (!(ncol0 + j < p.N)) x = 0.f;
+    a[j] = x;
+    q[j] = x * x;
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send_a = up ? a[i] : a[i + s];
+      const float keep_a = up ? a[i + s] : a[i];
+      a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
+      const float send_q = up ? q[i] : q[i + s];
+      const float keep_q = up ? q[i + s] : q[i];
+      q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
+    }
+  }
+  st0[lane] = a[0];
+  st1[lane] = q[0];
+}
+
+// generic path: any option, any alignment (cold)
+__device__ __forceinline__ void chunk_generic(const GemmKArgs& p, float (&v)[32], const ChunkCtx& cx, int lane,
+                                              float* st0, float* st1) {
+  const int ncol0 = cx.ncol0;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (ncol0 + j < p.N) v[j] += __ldg(p.bias + ncol0 + j);
+  }
+  if (p.act != CRIS_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+  }
+  if (p.resid != nullptr && cx.row_in) {
+    if (p.resid_fp32) {
+      const float* rp = reinterpret_cast<const float*>(p.resid) + cx.rrow + cx.dcol;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j < p.N) v[j] += rp[j];
+    } else {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + cx.rrow + cx.dcol;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
+    }
+  }
+  if (!cx.row_valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if (cx.row_in) {
+    if (p.d_fp32) {
+      float* base = reinterpret_cast<float*>(p.D) + cx.drow;
+      if (p.accumulate) {
+        float* ap = base + ((p.tap_mode == CRIS_TAP_WGRAD) ? cx.ztap * p.d_tap_n : 0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ncol0 + j < p.N) base[cx.dcol + j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + cx.drow + cx.dcol;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j < p.N) dp[j] = f2bf(v[j]);
+    }
+  }
+  if (p.colstats != nullptr) chunk_colstats(p, v, ncol0, lane, st0, st1);
+}
+
+// fast path: full chunk, 16-byte aligned rows, act in {none, relu}, bf16 residual
+template <int EPI>
+__device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], const ChunkCtx& cx, int lane,
+                                           float* st0, float* st1, const CUtensorMap* tmD, uint8_t* stg, int trow,
+                                           int b_in, int b_out, unsigned flags) {
+  if (flags & F_BIAS) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + cx.ncol0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 q = __ldg(bp + j);
+      v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+    }
+  }
+  if (flags & F_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if constexpr (EPI == EPI_RESID) {
+    if (cx.row_in) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + cx.rrow + cx.dcol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 q = rp[j];
+        const float2 e0 = unpack_bf16x2(q.x), e1 = unpack_bf16x2(q.y), e2 = unpack_bf16x2(q.z), e3 = unpack_bf16x2(q.w);
+        v[8 * j] += e0.x; v[8 * j + 1] += e0.y; v[8 * j + 2] += e1.x; v[8 * j + 3] += e1.y;
+        v[8 * j + 4] += e2.x; v[8 * j + 5] += e2.y; v[8 * j + 6] += e3.x; v[8 * j + 7] += e3.y;
+      }
+    }
+  }
+  if (!cx.row_valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if constexpr (EPI == EPI_ACCUM) {
+    if (cx.row_in) {
+      float* ap = reinterpret_cast<float*>(p.D) + cx.drow + ((flags & F_WGRAD) ? cx.ztap * p.d_tap_n : 0) +
+                  (long long)cx.ncol0 * p.d_col_stride;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(ap + (long long)j * p.d_col_stride, v[j]);
+    }
+  } else if (flags & F_TMA) {
+    // registers (one row per lane) -> 64-byte-swizzled smem box [32 rows x 64 B] -> one TMA tile store:
+    // coalesced, asynchronous, clipped at M / N by the tensor map; the LSU never sees 32 scattered rows
+    const int sw = (lane >> 1) & 3;
+    if (flags & F_DFP32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (lane == 0) ptx::bulk_wait_read0();  // the previous box has been read out of this buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ sw) << 4)) =
+              make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_4d(tmD, stg, cx.dcol + 16 * h, trow, b_in, b_out);
+          ptx::bulk_commit();
+        }
+      }
+    } else {
+      if (lane == 0) ptx::bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+        q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) = q;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_4d(tmD, stg, cx.dcol, trow, b_in, b_out);
+        ptx::bulk_commit();
+      }
+    }
+  } else {
+    if (cx.row_in) {
+      if (flags & F_DFP32) {
+        float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + cx.drow + cx.dcol);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + cx.drow + cx.dcol);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+          q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          dp[j] = q;
+        }
+      }
+    }
+  }
+  if constexpr (EPI == EPI_STATS) chunk_colstats(p, v, cx.ncol0, lane, st0, st1);
 }
 
 struct TileCoord {
@@ -94,10 +301,16 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKArgs& p, int tile, i
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (n fastest, so CTAs running
 // together share A rows in L2).  The smem ring keeps rolling across tiles; the TMEM accumulator is double
 // buffered so the epilogue of tile j overlaps the MMAs of tile j+1.
-template <int BN, int BK, bool A_MN, bool B_MN>
+#define CRIS_TRACE(j, slot)                                                                            \
+  do {                                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (j) < 32) p.trace[(j) * 16 + (slot)] = clock64(); \
+  } while (0)
+
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ GemmKArgs p, int tiles_n, int tiles_m, int total_tiles) {
+                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmKArgs p, int tiles_n,
+                   int tiles_m, int total_tiles) {
   using Cfg = TileCfg<BN, BK>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -108,6 +321,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   __shared__ float s_stats[4][2][BN];
+  __shared__ __align__(1024) uint8_t s_stage[EPI_WARPS][2048];  // per-warp 32 x 64 B box for TMA tile stores
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,21 +333,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == EPI_WARPS && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (p.tma_store) ptx::prefetch_tmap(&tmD);
   }
-  if (warp == 5) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == EPI_WARPS + 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
@@ -174,7 +389,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -213,13 +428,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3) =====================
-    uint8_t* Dbase = reinterpret_cast<uint8_t*>(p.D);
+    // ===================== epilogue (warps 0-7) =====================
+    // warp w reads TMEM lanes 32*(w%4) .. +31 (rows of the tile) and handles the 32-column chunks c with
+    // c % 2 == w / 4
+    const int wq = warp & 3, chalf = warp >> 2;
+    constexpr int NCHUNK = BN / 32;
+    const int my_last = (chalf < NCHUNK) ? (((NCHUNK - 1 - chalf) / 2) * 2 + chalf) : -1;
     int acc = 0;
+    unsigned flags = p.flags;
+    float alpha = p.alpha;
+    int ncols = p.N;
+    asm volatile("" : "+r"(flags), "+f"(alpha), "+r"(ncols));  // pin in ordinary registers (see F_* above)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
       const int n0 = tc.n0, ztap = tc.ztap;
-      const long long row = (long long)tc.m0 + warp * 32 + lane;
+      const long long row = (long long)tc.m0 + wq * 32 + lane;
       const bool row_in = row < p.M;
       const bool row_valid = row_in && interior_row(row, p.mask_hp, p.mask_wp);
       const int dcol0 = n0 + ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
@@ -231,156 +454,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         ptx::mbar_wait(&tmem_full[buf], ((uint32_t)acc >> 1) & 1u, 300 + buf);
         ptx::tc_fence_after();
       }
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS) + ((uint32_t)(warp * 32) << 16);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS) + ((uint32_t)(wq * 32) << 16);
+      if (has_acc && my_last < 0) {  // nothing to read for this warp (BN = 32): release the buffer right away
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+      }
+      CRIS_TRACE(acc, 0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf; c < NCHUNK; c += 2) {
         float v[32];
+        CRIS_TRACE(acc, 1 + (c >> 1) * 3);
         if (has_acc) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
+          CRIS_TRACE(acc, 2 + (c >> 1) * 3);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (flags & F_ALPHA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        if (c == BN / 32 - 1 && has_acc) {
+        if (c == my_last && has_acc) {
           // all TMEM reads of this tile are done: hand the accumulator buffer back to the MMA warp
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
         }
-        const int ncol0 = n0 + c * 32;  // logical column (bias / N bound)
-        if (ncol0 >= p.N) {
-          if (p.colstats != nullptr) {
-            s_stats[warp][0][c * 32 + lane] = 0.f;
-            s_stats[warp][1][c * 32 + lane] = 0.f;
-          }
+        ChunkCtx cx;
+        cx.ncol0 = n0 + c * 32;
+        cx.dcol = dcol0 + c * 32;
+        cx.drow = drow; cx.rrow = rrow; cx.ztap = ztap; cx.row_in = row_in; cx.row_valid = row_valid;
+        float* st0 = &s_stats[wq][0][c * 32];
+        float* st1 = &s_stats[wq][1][c * 32];
+        if (cx.ncol0 >= ncols) {
+          if (flags & F_STATS) { st0[lane] = 0.f; st1[lane] = 0.f; }
           continue;
         }
-        if (p.bias != nullptr) {
-          const float* bp = p.bias + ncol0;
-          if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(bp + j));
-              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + j < p.N) v[j] += __ldg(bp + j);
-          }
-        }
-        if (p.act != CRIS_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-        }
-        if (p.resid != nullptr && row_in) {
-          if (p.resid_fp32) {
-            const float* rp = reinterpret_cast<const float*>(p.resid) + rrow + dcol0 + c * 32;
-            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) v[j] += rp[j];
-            }
-          } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + rrow + dcol0 + c * 32;
-            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-                const float2 e0 = unpack_bf16x2(q.x), e1 = unpack_bf16x2(q.y), e2 = unpack_bf16x2(q.z),
-                             e3 = unpack_bf16x2(q.w);
-                v[j] += e0.x; v[j + 1] += e0.y; v[j + 2] += e1.x; v[j + 3] += e1.y;
-                v[j + 4] += e2.x; v[j + 5] += e2.y; v[j + 6] += e3.x; v[j + 7] += e3.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
-            }
-          }
-        }
-        if (!row_valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        // ---- store ----
-        if (row_in) {
-          if (p.d_fp32) {
-            float* dp = reinterpret_cast<float*>(Dbase) + drow + dcol0 + c * 32;
-            if (p.accumulate) {
-              float* ap = reinterpret_cast<float*>(Dbase) + drow +
-                          ((p.tap_mode == CRIS_TAP_WGRAD) ? ztap * p.d_tap_n : 0);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) atomicAdd(ap + (long long)(ncol0 + j) * p.d_col_stride, v[j]);
-            } else if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) dp[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(Dbase) + drow + dcol0 + c * 32;
-            if (ncol0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 q;
-                q.x = pack_bf16x2(v[j], v[j + 1]);
-                q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(dp + j) = q;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + j < p.N) dp[j] = f2bf(v[j]);
-            }
-          }
-        }
-        // ---- per-column batch statistics of the STORED (rounded) values ----
-        if (p.colstats != nullptr) {
-          float a[32], q[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = p.d_fp32 ? v[j] : bf2f(f2bf(v[j]));
-            if (!(ncol0 + j < p.N)) x = 0.f;
-            a[j] = x;
-            q[j] = x * x;
-          }
-          // transposing butterfly: after the 5 steps lane L holds the 32-lane total of column L
-#pragma unroll
-          for (int s = 16; s >= 1; s >>= 1) {
-            const bool up = (lane & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-              const float send_a = up ? a[i] : a[i + s];
-              const float keep_a = up ? a[i + s] : a[i];
-              a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, s);
-              const float send_q = up ? q[i] : q[i + s];
-              const float keep_q = up ? q[i + s] : q[i];
-              q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
-            }
-          }
-          s_stats[warp][0][c * 32 + lane] = a[0];
-          s_stats[warp][1][c * 32 + lane] = q[0];
-        }
+        if ((flags & F_FAST) && (cx.ncol0 + 32 <= ncols || ((flags & F_TMA) && EPI == EPI_PLAIN && !(flags & F_BIAS))))
+          chunk_fast<EPI>(p, v, cx, lane, st0, st1, &tmD, s_stage[warp], tc.m0 + wq * 32, tc.b_in, tc.b_out, flags);
+        else chunk_generic(p, v, cx, lane, st0, st1);
+        CRIS_TRACE(acc, 3 + (c >> 1) * 3);
       }
+      CRIS_TRACE(acc, 14);
       if (p.colstats != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int j = threadIdx.x; j < BN; j += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int j = threadIdx.x; j < BN; j += EPI_WARPS * 32) {
           if (n0 + j < p.N) {
             const float s0 = s_stats[0][0][j] + s_stats[1][0][j] + s_stats[2][0][j] + s_stats[3][0][j];
             const float s1 = s_stats[0][1][j] + s_stats[1][1][j] + s_stats[2][1][j] + s_stats[3][1][j];
@@ -390,16 +514,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             atomicAdd(dst + p.N + n0 + j, s1);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats is reused by the next tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // s_stats is reused by the next tile
       }
       if (has_acc) ++acc;
     }
+    if (lane == 0) ptx::bulk_wait0();  // every TMA tile store of this warp has been performed
   }
 
   // ---- teardown ----
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
@@ -422,25 +547,26 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // operand stored as [outer_extent][inner_extent] bf16 rows with pitch ld (elements) and batch stride
 static int make_tmap(CUtensorMap* tm, const void* base, long long inner_extent, long long outer_extent,
                      long long ld, long long batch, long long batch_stride, long long batch_in,
-                     long long batch_in_stride, int box_inner, int box_outer, CUtensorMapSwizzle swz) {
+                     long long batch_in_stride, int box_inner, int box_outer, CUtensorMapSwizzle swz, int esz = 2) {
   auto fn = get_encode_fn();
   CRIS_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   CRIS_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base not 16B aligned");
-  CRIS_CHECK_ARG((ld * 2) % 16 == 0, "GEMM operand pitch %lld elements is not a multiple of 16 bytes", ld);
+  CRIS_CHECK_ARG((ld * esz) % 16 == 0, "GEMM operand pitch %lld elements is not a multiple of 16 bytes", ld);
   if (batch_in <= 1) {
     batch_in = 1;
     batch_in_stride = ld * (outer_extent > 0 ? outer_extent : 1);
   }
   const long long batch_out = batch / batch_in;
   if (batch_out <= 1) batch_stride = batch_in_stride * batch_in;
-  CRIS_CHECK_ARG((batch_stride * 2) % 16 == 0 && (batch_in_stride * 2) % 16 == 0,
+  CRIS_CHECK_ARG((batch_stride * esz) % 16 == 0 && (batch_in_stride * esz) % 16 == 0,
                  "GEMM batch strides must be multiples of 16 bytes");
   cuuint64_t dims[4] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent, (cuuint64_t)batch_in,
                         (cuuint64_t)(batch_out > 0 ? batch_out : 1)};
-  cuuint64_t strides[3] = {(cuuint64_t)(ld * 2), (cuuint64_t)(batch_in_stride * 2), (cuuint64_t)(batch_stride * 2)};
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * esz), (cuuint64_t)(batch_in_stride * esz), (cuuint64_t)(batch_stride * esz)};
   cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(tm, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CRIS_CHECK_ARG(r == CUDA_SUCCESS,
@@ -474,8 +600,8 @@ static int pick_bn(const cris_gemm_args* a, int max_bn) {
   return a->N <= 32 ? 32 : 64;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN>
-static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
+template <int BN, int BK, bool A_MN, bool B_MN, int EPI>
+static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
   using Cfg = TileCfg<BN, BK>;
   CUtensorMap tmA, tmB;
   const long long bin = a->batch_inner > 1 ? a->batch_inner : 1;
@@ -504,7 +630,18 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
   if (rc) return rc;
   GemmKArgs kk = k;
   kk.nkb = (a->K + BK - 1) / BK;
-  auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN>;
+  // D tile stores through TMA whenever D is a dense 16-byte-aligned bf16/fp32 matrix (not the atomic paths)
+  CUtensorMap tmD = tmA;
+  const int desz = a->d_fp32 ? 4 : 2;
+  kk.tma_store = 0;
+  if (EPI != EPI_ACCUM && !a->accumulate && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 && (a->ldd * desz) % 16 == 0 &&
+      (a->batch <= 1 || ((a->strideD * desz) % 16 == 0 && (bin <= 1 || (a->strideD2 * desz) % 16 == 0)))) {
+    rc = make_tmap(&tmD, a->D, a->N, a->M, a->ldd, a->batch, a->strideD, bin, a->strideD2, 64 / desz, 32,
+                   CU_TENSOR_MAP_SWIZZLE_64B, desz);
+    if (rc) return rc;
+    kk.tma_store = 1;
+  }
+  auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, EPI>;
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
     CRIS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -514,14 +651,44 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
   const long long total = (long long)tiles_n * tiles_m * a->batch * kk.taps_z * kk.splits;
   CRIS_CHECK_ARG(total < (1ll << 31), "GEMM has too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kk, tiles_n, tiles_m, (int)total);
+  {
+    const int desz2 = a->d_fp32 ? 4 : 2;
+    const bool d_al = (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 && (a->ldd * desz2) % 16 == 0 &&
+                      (a->strideD * desz2) % 16 == 0 && (a->strideD2 * desz2) % 16 == 0;
+    const bool r_al = a->resid == nullptr || (!a->resid_fp32 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0 &&
+                                               (a->ldr * 2) % 16 == 0 && (a->strideR * 2) % 16 == 0 &&
+                                               (a->strideR2 * 2) % 16 == 0);
+    const bool b_al = a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
+    const bool epi_match = ((EPI == EPI_ACCUM) ? (a->d_fp32 && a->accumulate) : !a->accumulate) &&
+                           ((EPI == EPI_STATS) == (a->colstats != nullptr)) && ((EPI == EPI_RESID) == (a->resid != nullptr));
+    const bool fast = d_al && r_al && b_al && epi_match && (a->act == CRIS_ACT_NONE || a->act == CRIS_ACT_RELU) &&
+                      (EPI == EPI_ACCUM || a->d_col_stride <= 1);
+    kk.flags = (a->bias ? F_BIAS : 0) | (a->act == CRIS_ACT_RELU ? F_RELU : 0) | (fast ? F_FAST : 0) |
+               (kk.tma_store ? F_TMA : 0) | (a->d_fp32 ? F_DFP32 : 0) | (a->colstats ? F_STATS : 0) |
+               (a->tap_mode == CRIS_TAP_WGRAD ? F_WGRAD : 0) | (a->alpha != 1.0f ? F_ALPHA : 0);
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, kk, tiles_n, tiles_m, (int)total);
   CRIS_LAUNCH_OK();
   return 0;
+}
+
+// epilogue specialisation: wgrad-style fp32 atomics / BN statistics / bf16 residual / plain
+template <int BN, int BK, bool A_MN, bool B_MN>
+static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
+  if (a->accumulate) return launch_tc_epi<BN, BK, A_MN, B_MN, EPI_ACCUM>(a, k, stream);
+  if constexpr (!A_MN) {
+    if (a->colstats != nullptr && a->resid == nullptr) return launch_tc_epi<BN, BK, A_MN, B_MN, EPI_STATS>(a, k, stream);
+  }
+  if constexpr (BK == 64) {
+    if (a->resid != nullptr && a->colstats == nullptr) return launch_tc_epi<BN, BK, A_MN, B_MN, EPI_RESID>(a, k, stream);
+  }
+  return launch_tc_epi<BN, BK, A_MN, B_MN, EPI_PLAIN>(a, k, stream);
 }
 
 int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream);  // gemm_ref.cu
 
 static std::atomic<int> g_gemm_impl{0};
+static long long* g_trace = nullptr;  // debug timeline buffer (cris_debug_set_trace)
 
 int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
   CRIS_CHECK_ARG(a != nullptr, "null gemm args");
@@ -553,6 +720,7 @@ int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
   k.resid = a->resid; k.ldr = a->ldr; k.strideR = a->strideR; k.resid_fp32 = a->resid_fp32;
   k.mask_hp = a->mask_hp; k.mask_wp = a->mask_wp; k.colstats = a->colstats;
   k.d_col_stride = a->d_col_stride > 0 ? a->d_col_stride : 1;
+  k.trace = g_trace;
 
   const bool amn = a->a_mn != 0, bmn = a->b_mn != 0;
   const bool k32 = (a->K <= 32) && !amn && !bmn;  // stem convs: 32 input channels per tap
@@ -589,5 +757,6 @@ int cris_gemm(const cris_gemm_args* args, void* stream) {
   return cris::gemm_dispatch(args, reinterpret_cast<cudaStream_t>(stream));
 }
 void cris_set_gemm_impl(int impl) { cris::g_gemm_impl.store(impl); }
+void cris_debug_set_trace(void* dev_buf) { cris::g_trace = reinterpret_cast<long long*>(dev_buf); }
 int cris_get_gemm_impl(void) { return cris::g_gemm_impl.load(); }
 }

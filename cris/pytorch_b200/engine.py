@@ -158,6 +158,7 @@ class Engine:
         self.probe_events: List = []
         # whole-pass CUDA graphs (forward graph + backward graph per input shape): removes ~2000 host launches/step
         self.use_graphs = os.environ.get("CRIS_B200_GRAPHS", "1") != "0"
+        self.gemm_log: Optional[list] = None  # profiling: (M,N,K,batch,...) of every GEMM launch, in order
         self.force_sync_bn = False  # tests: exercise the cross-rank BN exchange without SyncBatchNorm modules
         self.graphs: Dict[tuple, "GraphedStep"] = {}
         self._counter: Optional[torch.Tensor] = None
@@ -427,6 +428,9 @@ class Run:
             g.mask_hp, g.mask_wp = mask_geom[1] + 2, mask_geom[2] + 2
         g.colstats = colstats
         g.a_rows, g.b_rows, g.d_col_stride = a_rows, b_rows, d_col_stride
+        if self.e.gemm_log is not None:
+            self.e.gemm_log.append((M, N, K, batch, a_mn, b_mn, taps if tap_mode else 1, tap_mode, splits, int(D.fp32),
+                                    int(resid is not None), int(colstats is not None)))
         gemm(g)
 
     @staticmethod

@@ -34,6 +34,8 @@ int  cris_device_check(void);               /* 0 iff current device is sm_100 (B
 /* 0 = tcgen05 GEMM (product path), 1 = SIMT reference GEMM (differential testing only) */
 void cris_set_gemm_impl(int impl);
 int  cris_get_gemm_impl(void);
+/* debug: device buffer of 32*16 int64 receiving per-tile clock64 stamps of CTA 0 of every following GEMM (NULL = off) */
+void cris_debug_set_trace(void* dev_buf);
 uint64_t cris_launch_count(void);           /* kernels launched by this library so far    */
 void cris_add_launch_count(uint64_t n);     /* a replayed CUDA graph adds the launches it contains */
 

@@ -364,6 +364,7 @@ static void perf(int only = -1) {
       {"conv3x3 64x(106x106) 512->256", 64 * 106 * 106, 256, 512, 9, 106, 106, 0, 0},
       {"conv3x3 64x(54x54) 512->512", 64 * 54 * 54, 512, 512, 9, 54, 54, 0, 0},
       {"conv3x3 64x(106x106) 64->64", 64 * 106 * 106, 64, 64, 9, 106, 106, 0, 0},
+      {"conv1x1 64x(106x106) 64->256", 64 * 106 * 106, 256, 64, 1, 106, 106, 0, 0},
       {"conv1x1 64x(106x106) 256->64", 64 * 106 * 106, 64, 256, 1, 106, 106, 0, 0},
       {"dgrad 43264x512x2048 (B MN)", 43264, 512, 2048, 1, 0, 0, 0, 1},
       {"wgrad 512x512x43264 (A,B MN)", 512, 512, 43264, 1, 0, 0, 1, 1},
@@ -396,6 +397,21 @@ static void perf(int only = -1) {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= iters;
     double fl = 2.0 * q.M * q.N * (double)q.K * q.taps;
     printf("PERF %-36s %8.3f ms  %8.1f TFLOP/s\n", q.name, ms, fl / ms * 1e-9);
+    if (getenv("CRIS_B200_TRACE")) {
+      long long* tr; CK(cudaMalloc(&tr, 32 * 16 * 8)); CK(cudaMemset(tr, 0, 32 * 16 * 8));
+      cris_debug_set_trace(tr);
+      cris_gemm(&a, nullptr); CK(cudaDeviceSynchronize());
+      cris_debug_set_trace(nullptr);
+      long long h[32 * 16]; CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+      const long long t0 = h[0];
+      printf("  epilogue warp 0 timeline (SM cycles): tile | start | per chunk: before-ld after-ld after-process ... | end\n");
+      for (int j = 0; j < 10; ++j) {
+        printf("  %3d |", j);
+        for (int k2 = 0; k2 < 15; ++k2) if (h[j * 16 + k2]) printf(" %7lld", h[j * 16 + k2] - t0);
+        printf("\n");
+      }
+      cudaFree(tr);
+    }
     cudaFree(A); cudaFree(B); cudaFree(D);
   }
 }

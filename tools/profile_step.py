@@ -39,10 +39,14 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
+    eng = model._get_engine()
+    eng.gemm_log = []
     torch.cuda.cudart().cudaProfilerStart()
     step()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
+    import json
+    json.dump(eng.gemm_log, open(os.path.join(REPO, 'gpurun_out', 'gemm_log.json'), 'w'))
 
 
 if __name__ == "__main__":
