@@ -164,6 +164,13 @@ class Engine:
         self._counter: Optional[torch.Tensor] = None
         _lib.lib()
 
+    @classmethod
+    def bare(cls) -> "Engine":
+        """An engine without a model: used by the per-op tests to drive single building blocks."""
+        class _NoModel(nn.Module):
+            dropout_p = 0.0
+        return cls(_NoModel())
+
     def step_counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != device:
             self._counter = torch.zeros(1, dtype=torch.int64, device=device)

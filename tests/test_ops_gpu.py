@@ -12,18 +12,8 @@ pytestmark = pytest.mark.gpu
 def _mk_run(params=None, buffers=None, training=True, p_drop=0.0):
     from cris.pytorch_b200 import engine as E
 
-    class _Eng:
-        def __init__(self):
-            self.packed = E.PackedWeights()
-            self.consts = {}
-            self.debug_taps = None
-            self.probe_name, self.probe_events = None, []
-            self.step = 0
-
-        const = E.Engine.const
-
     r = object.__new__(E.Run)
-    r.e = _Eng()
+    r.e = E.Engine.bare()
     r.dev = torch.device("cuda")
     r.training, r.record = training, training
     r.tape, r.pgrad = [], {}
