@@ -44,11 +44,13 @@ class GemmArgs(C.Structure):
 # signature mini-language: p = pointer, q = int64, i = int32, f = float, d = double, u = uint64
 _T = {"p": C.c_void_p, "q": C.c_int64, "i": C.c_int32, "f": C.c_float, "d": C.c_double, "u": C.c_uint64}
 _SIGS = {
-    "cris_col_reduce": "ipqipqpqpqippqiiiipip",
+    "cris_col_reduce": "ipqipqpqpqippppqiiiipip",
+    "cris_bn_finalize_fwd": "piipdppffppppppp",
+    "cris_stats_finalize_bwd": "piipppp",
     "cris_bn_reduce_partials": "piipp",
     "cris_bn_coeffs": "pdppffppppppiip",
     "cris_bn_apply": "pqpppqpqqiiiip",
-    "cris_bn_bwd_apply": "pqpqpqppppdpqpqiqiiiip",
+    "cris_bn_bwd_apply": "pqpqpqpppppdpqpqiqiiiip",
     "cris_layernorm_fwd": "piqpppqipiqpqppqifp",
     "cris_layernorm_bwd": "piqpqpiqppppiqiqip",
     "cris_avgpool2_fwd": "pqpqiiiip",

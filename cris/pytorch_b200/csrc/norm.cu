@@ -19,6 +19,7 @@ struct ColReduceArgs {
   const void* y;  long long ldy;                 // post-activation output (mode 1, relu mask), bf16
   const void* x;  long long ldx; int x_fp32;     // pre-normalisation input (modes 1, 3)
   const float* mean; const float* rstd;          // per-column (mode 1) or per-row (mode 3)
+  const float* scale; const float* shift;        // mode 1 with y == NULL: ReLU mask recomputed as x*scale+shift > 0
   long long rows; int C; int relu; int hp, wp;
   float* partials;
 };
@@ -38,10 +39,14 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
 #pragma unroll
     for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
     const int c = g * 8;
-    float mu[8], rs[8];
+    float mu[8], rs[8], sc[8], sh[8];
     if (MODE == 1) {
       ld8f(p.mean + c, mu);
       ld8f(p.rstd + c, rs);
+      if (p.relu && p.y == nullptr) {
+        ld8f(p.scale + c, sc);
+        ld8f(p.shift + c, sh);
+      }
     }
     if (tr < R) {
       // U rows per trip: all loads of a trip are issued before any is consumed (memory-level parallelism)
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
           if (ok[u]) {
             ld8x(p.a, r * p.lda + c, p.a_fp32, a[u]);
             if (MODE == 1 || MODE == 3) ld8x(p.x, r * p.ldx + c, p.x_fp32, xv[u]);
-            if (MODE == 1 && p.relu) ld8(reinterpret_cast<const __nv_bfloat16*>(p.y) + r * p.ldy + c, yv[u]);
+            if (MODE == 1 && p.relu && p.y != nullptr) ld8(reinterpret_cast<const __nv_bfloat16*>(p.y) + r * p.ldy + c, yv[u]);
             if (MODE == 3 && p.a2 != nullptr) ld8(reinterpret_cast<const __nv_bfloat16*>(p.a2) + r * p.lda2 + c, yv[u]);
           }
         }
@@ -72,8 +77,13 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
             for (int i = 0; i < 8; ++i) s0[i] += a[u][i];
           } else if (MODE == 1) {
             if (p.relu) {
+              if (p.y != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) if (!(yv[u][i] > 0.f)) a[u][i] = 0.f;
+                for (int i = 0; i < 8; ++i) if (!(yv[u][i] > 0.f)) a[u][i] = 0.f;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (!(fmaf(xv[u][i], sc[i], sh[i]) > 0.f)) a[u][i] = 0.f;
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] += a[u][i] * (xv[u][i] - mu[i]) * rs[i]; }
@@ -207,7 +217,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long l
                                     const __nv_bfloat16* __restrict__ y, long long ldy,
                                     const __nv_bfloat16* __restrict__ x, long long ldx,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ sums, float inv_count,
                                     __nv_bfloat16* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dres,
                                     long long lddres, int dres_accumulate, long long rows, int C, int relu, int hp,
                                     int wp) {
@@ -221,14 +232,24 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long l
     if (interior_row(r, hp, wp)) {
       float xv[8], mu[8], is[8], ga[8], s0[8], s1[8];
       ld8(dy + r * lddy + c, dz);
-      if (relu) {
-        float yv[8];
-        ld8(y + r * ldy + c, yv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) dz[k] = 0.f;
-      }
       ld8(x + r * ldx + c, xv);
       ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga);
+      if (relu) {
+        if (y != nullptr) {
+          float yv[8];
+          ld8(y + r * ldy + c, yv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) dz[k] = 0.f;
+        } else {  // no residual: the forward value was fma(x, scale, shift) with scale = gamma*invstd
+          float be[8];
+          ld8f(beta + c, be);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float scl = ga[k] * is[k];
+            if (!(fmaf(xv[k], scl, be[k] - mu[k] * scl) > 0.f)) dz[k] = 0.f;
+          }
+        }
+      }
       ld8f(sums + c, s0); ld8f(sums + C + c, s1);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -367,6 +388,76 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- fused small kernels (one launch instead of three) --------------------------------------------------
+// forward: partials[n_tiles][2][C] -> sums -> scale/shift/mean/invstd (+ running statistics)
+__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ partials, int n_tiles, int C,
+                                                              float* __restrict__ sums, double count,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, float momentum, float* running_mean,
+                                                              float* running_var, float* scale, float* shift,
+                                                              float* mean_out, float* invstd_out) {
+  __shared__ float sm[8][2][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int t = grp; t < n_tiles; t += 8) {
+      s0 += partials[(size_t)t * 2 * C + c];
+      s1 += partials[(size_t)t * 2 * C + C + c];
+    }
+  }
+  sm[grp][0][lane] = s0;
+  sm[grp][1][lane] = s1;
+  __syncthreads();
+  if (grp == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { a += sm[g][0][lane]; b += sm[g][1][lane]; }
+    sums[c] = a;
+    sums[C + c] = b;
+    const double m = (double)a / count;
+    double v = (double)b / count - m * m;
+    if (v < 0) v = 0;
+    if (running_mean != nullptr) {
+      const double unb = count > 1 ? v * count / (count - 1) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+    const float inv = rsqrtf((float)v + eps);
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)m * sc;
+    mean_out[c] = (float)m;
+    invstd_out[c] = inv;
+  }
+}
+// backward: partials -> sums (for dx) and the parameter gradients dbeta = sum dz, dgamma = sum dz*xhat
+__global__ void __launch_bounds__(256) stats_finalize_bwd_kernel(const float* __restrict__ partials, int n_tiles, int C,
+                                                                 float* __restrict__ sums, float* __restrict__ g0,
+                                                                 float* __restrict__ g1) {
+  __shared__ float sm[8][2][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int t = grp; t < n_tiles; t += 8) {
+      s0 += partials[(size_t)t * 2 * C + c];
+      s1 += partials[(size_t)t * 2 * C + C + c];
+    }
+  }
+  sm[grp][0][lane] = s0;
+  sm[grp][1][lane] = s1;
+  __syncthreads();
+  if (grp == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { a += sm[g][0][lane]; b += sm[g][1][lane]; }
+    if (sums != nullptr) { sums[c] = a; sums[C + c] = b; }
+    if (g0 != nullptr) g0[c] = a;
+    if (g1 != nullptr) g1[c] = b;
+  }
+}
+
 }  // namespace cris
 
 using namespace cris;
@@ -375,10 +466,11 @@ extern "C" {
 
 int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void* a2, int64_t lda2, const void* y,
                     int64_t ldy, const void* x, int64_t ldx, int x_fp32, const float* mean, const float* rstd,
-                    int64_t rows, int C, int relu, int hp, int wp, float* partials, int n_blocks, void* stream) {
+                    const float* scale, const float* shift, int64_t rows, int C, int relu, int hp, int wp,
+                    float* partials, int n_blocks, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0 && C <= 2048, "col_reduce: C=%d must be a multiple of 8 and <= 2048", C);
   CRIS_CHECK_ARG(n_blocks >= 1, "col_reduce: n_blocks");
-  ColReduceArgs p{a, lda, a_fp32, a2, lda2, y, ldy, x, ldx, x_fp32, mean, rstd, rows, C, relu, hp, wp, partials};
+  ColReduceArgs p{a, lda, a_fp32, a2, lda2, y, ldy, x, ldx, x_fp32, mean, rstd, scale, shift, rows, C, relu, hp, wp, partials};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (mode) {
     case 0: col_reduce_kernel<0><<<n_blocks, 256, 0, s>>>(p); break;
@@ -398,6 +490,20 @@ int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* su
   return 0;
 }
 
+int cris_bn_finalize_fwd(const float* partials, int n_tiles, int C, float* sums, double count, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  bn_finalize_fwd_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partials, n_tiles, C, sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_stats_finalize_bwd(const float* partials, int n_tiles, int C, float* sums, float* g0, float* g1, void* stream) {
+  stats_finalize_bwd_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles, C, sums,
+                                                                                              g0, g1);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
 int cris_bn_coeffs(const float* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
                    int C, int training, void* stream) {
@@ -419,14 +525,14 @@ int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* s
 }
 
 int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
-                      const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
-                      void* dx, int64_t lddx, void* dres, int64_t lddres, int dres_accumulate, int64_t rows, int C,
-                      int relu, int hp, int wp, void* stream) {
+                      const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const float* sums, double count, void* dx, int64_t lddx, void* dres, int64_t lddres,
+                      int dres_accumulate, int64_t rows, int C, int relu, int hp, int wp, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   const long long work = rows * (C / 8);
   bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), ldy,
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean, invstd, gamma, sums, (float)(1.0 / count),
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean, invstd, gamma, beta, sums, (float)(1.0 / count),
       reinterpret_cast<__nv_bfloat16*>(dx), lddx, reinterpret_cast<__nv_bfloat16*>(dres), lddres, dres_accumulate,
       rows, C, relu, hp, wp);
   CRIS_LAUNCH_OK();

@@ -361,10 +361,21 @@ class Run:
         return self.e.packed.get(name, self.P[name], as_matrix)
 
     def pg(self, name) -> torch.Tensor:
+        """fp32 gradient buffer of a parameter: a view of ONE zero-filled flat buffer (one memset per backward)."""
         g = self.pgrad.get(name)
         if g is None:
-            g = torch.zeros_like(self.P[name], dtype=torch.float32)
-            self.pgrad[name] = g
+            if not self.pgrad:
+                total, offs = 0, {}
+                for k, p in self.P.items():
+                    offs[k] = total
+                    total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+                flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+                for k, p in self.P.items():
+                    self.pgrad[k] = flat[offs[k]:offs[k] + p.numel()].view(p.shape)
+                g = self.pgrad.get(name)
+            if g is None:
+                g = torch.zeros_like(self.P[name], dtype=torch.float32)
+                self.pgrad[name] = g
         return g
 
     def on_backward(self, fn):
@@ -460,7 +471,7 @@ class Run:
             cw = min(2048, wpad - c0)
             pt = self.f32(nb * 2 * cw)
             call("cris_col_reduce", 2, m.ptr + c0 * m.esize, m.ld, int(m.fp32), None, 0, None, 0, None, 0, 0, None, None,
-                 m.rows, cw, 0, hp, wp, pt.data_ptr(), nb)
+                 None, None, m.rows, cw, 0, hp, wp, pt.data_ptr(), nb)
             sm = self.f32(2 * cw)
             call("cris_bn_reduce_partials", pt.data_ptr(), nb, cw, sm.data_ptr())
             out[c0:c0 + cw].copy_(sm[:cw])
@@ -486,15 +497,19 @@ class Run:
             if partials is None:
                 n_tiles = max(1, min(592, z.rows // 64))
                 partials = self.f32(n_tiles * 2 * C)
-                call("cris_col_reduce", 0, z.ptr, z.ld, 0, None, 0, None, 0, None, 0, 0, None, None, z.rows, C, 0,
-                     z.hp, z.wp, partials.data_ptr(), n_tiles)
+                call("cris_col_reduce", 0, z.ptr, z.ld, 0, None, 0, None, 0, None, 0, 0, None, None, None, None, z.rows,
+                     C, 0, z.hp, z.wp, partials.data_ptr(), n_tiles)
             sums = self.f32(2 * C)
-            call("cris_bn_reduce_partials", partials.data_ptr(), n_tiles, C, sums.data_ptr())
             if self.sync_bn:
+                call("cris_bn_reduce_partials", partials.data_ptr(), n_tiles, C, sums.data_ptr())
                 self.allreduce(sums)
-            call("cris_bn_coeffs", sums.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM,
-                 rm.data_ptr(), rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * C, coef.data_ptr() + 8 * C,
-                 coef.data_ptr() + 12 * C, C, 1)
+                call("cris_bn_coeffs", sums.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM,
+                     rm.data_ptr(), rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * C, coef.data_ptr() + 8 * C,
+                     coef.data_ptr() + 12 * C, C, 1)
+            else:
+                call("cris_bn_finalize_fwd", partials.data_ptr(), n_tiles, C, sums.data_ptr(), count, gamma.data_ptr(),
+                     beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(), rv.data_ptr(), coef.data_ptr(),
+                     coef.data_ptr() + 4 * C, coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C)
             nbt = self.Bf.get(prefix + ".num_batches_tracked")
             if nbt is not None:
                 nbt.add_(1)
@@ -512,14 +527,15 @@ class Run:
                 return
             nb = max(1, min(592, z.rows // 64))
             part = self.f32(nb * 2 * C)
-            call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, y.ptr, y.ld, z.ptr, z.ld, 0, coef.data_ptr() + 8 * C,
-                 coef.data_ptr() + 12 * C, z.rows, C, int(relu), z.hp, z.wp, part.data_ptr(), nb)
+            # without a residual the ReLU mask is recomputed from z (x*scale+shift > 0): y is not re-read
+            ymask = y if (resid is not None or not relu) else None
+            call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, ymask.ptr if ymask else None, ymask.ld if ymask else 0,
+                 z.ptr, z.ld, 0, coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C, coef.data_ptr(),
+                 coef.data_ptr() + 4 * C, z.rows, C, int(relu), z.hp, z.wp, part.data_ptr(), nb)
             bs = self.f32(2 * C)
-            call("cris_bn_reduce_partials", part.data_ptr(), nb, C, bs.data_ptr())
             # parameter gradients are LOCAL sums (DDP averages them), dx needs the GLOBAL sums
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
-            call("cris_elementwise", 0, bs.data_ptr(), 1, C, None, 0, 0, gb.data_ptr(), 1, C, 1, C, 0.0, 0, None)
-            call("cris_elementwise", 0, bs.data_ptr() + 4 * C, 1, C, None, 0, 0, gg.data_ptr(), 1, C, 1, C, 0.0, 0, None)
+            call("cris_stats_finalize_bwd", part.data_ptr(), nb, C, bs.data_ptr(), gb.data_ptr(), gg.data_ptr())
             if self.sync_bn:
                 self.allreduce(bs)
             dz = self.new(z.rows, C, False, z.geom)
@@ -527,9 +543,9 @@ class Run:
             if resid is not None and resid.need_grad:
                 slot, acc = self.grad_slot(resid)
                 dres_ptr, dres_ld, dres_acc = slot.ptr, slot.ld, int(acc)
-            call("cris_bn_bwd_apply", dy.ptr, dy.ld, y.ptr, y.ld, z.ptr, z.ld, coef.data_ptr() + 8 * C,
-                 coef.data_ptr() + 12 * C, gamma.data_ptr(), bs.data_ptr(), count, dz.ptr, dz.ld, dres_ptr, dres_ld,
-                 dres_acc, z.rows, C, int(relu), z.hp, z.wp)
+            call("cris_bn_bwd_apply", dy.ptr, dy.ld, ymask.ptr if ymask else None, ymask.ld if ymask else 0, z.ptr, z.ld,
+                 coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C, gamma.data_ptr(), beta.data_ptr(), bs.data_ptr(),
+                 count, dz.ptr, dz.ld, dres_ptr, dres_ld, dres_acc, z.rows, C, int(relu), z.hp, z.wp)
             self.set_grad(z, dz)
 
         if self.training:
@@ -712,13 +728,10 @@ class Run:
             nb = max(1, min(592, x.rows // 64))
             pt = self.f32(nb * 2 * C)
             call("cris_col_reduce", 3, d1.ptr, d1.ld, int(d1.fp32), d2.ptr if d2 else None, d2.ld if d2 else 0, None, 0,
-                 x.ptr, x.ld, int(x.fp32), stats.data_ptr(), stats.data_ptr() + 4 * x.rows, x.rows, C, 0, 0, 0,
+                 x.ptr, x.ld, int(x.fp32), stats.data_ptr(), stats.data_ptr() + 4 * x.rows, None, None, x.rows, C, 0, 0, 0,
                  pt.data_ptr(), nb)
-            sm = self.f32(2 * C)
-            call("cris_bn_reduce_partials", pt.data_ptr(), nb, C, sm.data_ptr())
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
-            call("cris_elementwise", 0, sm.data_ptr(), 1, C, None, 0, 0, gb.data_ptr(), 1, C, 1, C, 0.0, 0, None)
-            call("cris_elementwise", 0, sm.data_ptr() + 4 * C, 1, C, None, 0, 0, gg.data_ptr(), 1, C, 1, C, 0.0, 0, None)
+            call("cris_stats_finalize_bwd", pt.data_ptr(), nb, C, None, gb.data_ptr(), gg.data_ptr())
             if x.need_grad:
                 slot, acc = self.grad_slot(x)
                 call("cris_layernorm_bwd", d1.ptr, int(d1.fp32), d1.ld, d2.ptr if d2 else None, d2.ld if d2 else 0,

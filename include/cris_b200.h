@@ -105,14 +105,22 @@ int cris_gemm_args_last_offset(void);  /* offsetof(cris_gemm_args, d_col_stride)
  * Column reduction of a [rows, C] matrix into partials[n_blocks][2][C] (fp32):
  *   mode 0: (sum x, sum x^2)                       batch statistics (nn.BatchNorm2d training,
  *                                                  model/clip.py:18-26,171-183; model/layers.py:8-16,262)
- *   mode 1: (sum dz, sum dz*xhat), dz = dy*(y>0)   BatchNorm backward (batch_norm_backward_reduce)
+ *   mode 1: (sum dz, sum dz*xhat), dz = dy*(y>0)   BatchNorm backward (batch_norm_backward_reduce); with y == NULL the
+ *                                                  ReLU mask is recomputed as x*scale[c]+shift[c] > 0 (no residual)
  *   mode 2: (sum dy, -)                            bias gradients of nn.Linear / Conv2d(bias=True)
  *   mode 3: (sum dy, sum dy*xhat), per-ROW mean/rstd   LayerNorm gamma/beta gradients
  * hp/wp > 0 skips the zero border rows of a padded-NHWC matrix.
  */
 int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void* a2, int64_t lda2, const void* y,
                     int64_t ldy, const void* x, int64_t ldx, int x_fp32, const float* mean, const float* rstd,
-                    int64_t rows, int C, int relu, int hp, int wp, float* partials, int n_blocks, void* stream);
+                    const float* scale, const float* shift, int64_t rows, int C, int relu, int hp, int wp,
+                    float* partials, int n_blocks, void* stream);
+/* fused: partials -> sums -> scale/shift/mean/invstd + running-stat update (single-rank BatchNorm forward) */
+int cris_bn_finalize_fwd(const float* partials, int n_tiles, int C, float* sums, double count, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* fused: partials -> sums[2][C] (optional) and two parameter-gradient vectors g0 = sum0, g1 = sum1 (optional) */
+int cris_stats_finalize_bwd(const float* partials, int n_tiles, int C, float* sums, float* g0, float* g1, void* stream);
 /* sums[2][C] = sum over tiles of partials[n_tiles][2][C] (GEMM-epilogue or col_reduce partials) */
 int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums, void* stream);
 /*
@@ -128,9 +136,9 @@ int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* s
                   void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream);
 /* dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count); optional dres (+)= dz (residual branch) */
 int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
-                      const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
-                      void* dx, int64_t lddx, void* dres, int64_t lddres, int dres_accumulate, int64_t rows, int C,
-                      int relu, int hp, int wp, void* stream);
+                      const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const float* sums, double count, void* dx, int64_t lddx, void* dres, int64_t lddres,
+                      int dres_accumulate, int64_t rows, int C, int relu, int hp, int wp, void* stream);
 
 /* ---- LayerNorm (nn.LayerNorm; model/clip.py:226-231, model/layers.py:199-216) --------------- */
 /* y = LN(x); optional y2 = y + add[row % add_period] (bf16) — the "+ positional encoding" copy for q/k */
