@@ -137,10 +137,18 @@ def gemm(args: GemmArgs):
         raise RuntimeError(f"libcris_b200 cris_gemm failed: {lib().cris_last_error().decode()}")
 
 
+_checked_devices = set()
+
+
 def device_check():
+    """Raise unless the current device is sm_100; cached per device (cudaGetDeviceProperties is slow and jittery)."""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    if dev in _checked_devices:
+        return
     rc = lib().cris_device_check()
     if rc != 0:
         raise RuntimeError(f"libcris_b200: {lib().cris_last_error().decode()}")
+    _checked_devices.add(dev)
 
 
 def launch_count() -> int:

@@ -290,10 +290,20 @@ class GraphedStep:
 class _GraphFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gs: GraphedStep, img, word, mask, *params):
+        prof = os.environ.get("CRIS_B200_HOSTPROF") == "1"
+        if prof:
+            import time
+            t0 = time.perf_counter()
         gs.img.copy_(img)
         gs.word.copy_(word)
         gs.mask.copy_(mask)
+        if prof:
+            t1 = time.perf_counter()
         gs.gf.replay()
+        if prof:
+            t2 = time.perf_counter()
+            if t2 - t0 > 0.01:
+                print(f"[hostprof] input copies {1e3 * (t1 - t0):.1f} ms, graph launch {1e3 * (t2 - t1):.1f} ms", flush=True)
         _lib.lib().cris_add_launch_count(gs.n_fwd)
         ctx.gs = gs
         pred, mask_out, loss = gs.pred.detach(), gs.mask_out.detach(), gs.loss.detach().clone()
