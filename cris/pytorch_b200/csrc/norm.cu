@@ -25,7 +25,7 @@ struct ColReduceArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) {
+__global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs p) {
   __shared__ float sm[256 * 16];
   const int G = p.C / 8;
   const int Gp = G < 256 ? G : 256;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const ColReduceArgs p) 
     }
     if (tr < R) {
       // U rows per trip: all loads of a trip are issued before any is consumed (memory-level parallelism)
-      constexpr int U = (MODE == 1) ? 3 : 4;
+      constexpr int U = (MODE == 1) ? 2 : 4;
       for (long long rb = r0 + tr; rb < r1; rb += (long long)R * U) {
         float a[U][8], xv[U][8], yv[U][8];
         bool ok[U];
