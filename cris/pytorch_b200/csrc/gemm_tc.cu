@@ -284,10 +284,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKArgs& p, int tile, i
   int z = rest / tiles_m;
   t.n0 = nt * BNv;
   t.m0 = mt * BM;
-  t.split = z % p.splits;
-  z /= p.splits;
+  // tap fastest: the 9 taps of one K-range run on neighbouring CTAs at the same time, so the wgrad operands
+  // (the same rows, shifted) are fetched from HBM once and re-read from L2
   t.ztap = z % p.taps_z;
-  const int batch = z / p.taps_z;
+  z /= p.taps_z;
+  t.split = z % p.splits;
+  const int batch = z / p.splits;
   t.b_in = batch % p.batch_inner;
   t.b_out = batch / p.batch_inner;
   const int kb_per_split = (p.nkb + p.splits - 1) / p.splits;

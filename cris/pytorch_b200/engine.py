@@ -763,15 +763,24 @@ class Run:
             if g is None:
                 return
             # identity branch: grad(x) (+)= g ; dropout branch: grad(h) (+)= dropout_mask(g)
-            slot, acc = self.grad_slot(h)
-            if acc:
-                t = self.new(h.rows, h.C, slot.fp32)
-                self.ew(2, g, None, t, p, sd)
-                self.ew(0, slot, t, slot)
+            hroot = h.root if h.root is not None else h
+            if p == 0 and hroot.gbuf is None and h.root is None and g.ld == h.C:
+                # no dropout: grad(h) IS grad(out) (fp32); its consumers (LayerNorm / Linear backward) accept fp32
+                self.set_grad(h, g)
             else:
-                self.ew(2, g, None, slot, p, sd)
-            slot, acc = self.grad_slot(x)
-            self.ew(0, g, slot if acc else None, slot)
+                slot, acc = self.grad_slot(h)
+                if acc:
+                    t = self.new(h.rows, h.C, slot.fp32)
+                    self.ew(2, g, None, t, p, sd)
+                    self.ew(0, slot, t, slot)
+                else:
+                    self.ew(2, g, None, slot, p, sd)
+            root = x.root if x.root is not None else x
+            if root.gbuf is None and x.root is None and g.ld == x.C and g.fp32 == x.fp32:
+                self.set_grad(x, g)  # first contribution: alias grad(out) instead of copying it
+            else:
+                slot, acc = self.grad_slot(x)
+                self.ew(0, g, slot if acc else None, slot)
 
         if self.training:
             self.on_backward(bwd)
