@@ -465,12 +465,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll 1
       for (int c = chalf; c < NCHUNK; c += 2) {
         float v[32];
-        CRIS_TRACE(acc, 1 + (c >> 1) * 3);
         if (has_acc) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
           ptx::tmem_ld_wait();
-          CRIS_TRACE(acc, 2 + (c >> 1) * 3);
 #pragma unroll
           if (flags & F_ALPHA) {
 #pragma unroll
@@ -501,7 +499,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if ((flags & F_FAST) && (cx.ncol0 + 32 <= ncols || ((flags & F_TMA) && EPI == EPI_PLAIN && !(flags & F_BIAS))))
           chunk_fast<EPI>(p, v, cx, lane, st0, st1, &tmD, s_stage[warp], tc.m0 + wq * 32, tc.b_in, tc.b_out, flags);
         else chunk_generic(p, v, cx, lane, st0, st1);
-        CRIS_TRACE(acc, 3 + (c >> 1) * 3);
       }
       CRIS_TRACE(acc, 14);
       if (p.colstats != nullptr) {

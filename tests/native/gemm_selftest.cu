@@ -398,16 +398,16 @@ static void perf(int only = -1) {
     double fl = 2.0 * q.M * q.N * (double)q.K * q.taps;
     printf("PERF %-36s %8.3f ms  %8.1f TFLOP/s\n", q.name, ms, fl / ms * 1e-9);
     if (getenv("CRIS_B200_TRACE")) {
-      long long* tr; CK(cudaMalloc(&tr, 32 * 16 * 8)); CK(cudaMemset(tr, 0, 32 * 16 * 8));
+      long long* tr; CK(cudaMalloc(&tr, 64 * 16 * 8)); CK(cudaMemset(tr, 0, 64 * 16 * 8));
       cris_debug_set_trace(tr);
       cris_gemm(&a, nullptr); CK(cudaDeviceSynchronize());
       cris_debug_set_trace(nullptr);
-      long long h[32 * 16]; CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+      long long h[64 * 16]; CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
       const long long t0 = h[0];
-      printf("  epilogue warp 0 timeline (SM cycles): tile | start | per chunk: before-ld after-ld after-process ... | end\n");
+      printf("  epilogue warp 0 timeline (SM cycles): tile | slot:cycle (0 = tile start, 14 = tile end)\n");
       for (int j = 0; j < 10; ++j) {
         printf("  %3d |", j);
-        for (int k2 = 0; k2 < 15; ++k2) if (h[j * 16 + k2]) printf(" %7lld", h[j * 16 + k2] - t0);
+        for (int k2 = 0; k2 < 15; ++k2) if (h[j * 16 + k2]) printf(" %d:%lld", k2, h[j * 16 + k2] - t0);
         printf("\n");
       }
       cudaFree(tr);
