@@ -98,6 +98,12 @@ def lib():
         L.cris_set_gemm_impl.argtypes = [C.c_int]
         L.cris_add_launch_count.argtypes = [C.c_uint64]
         L.cris_add_launch_count.restype = None
+        L.cris_peer_buffer_bytes.restype = C.c_size_t
+        L.cris_peer_buffer_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+        L.cris_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.cris_peer_buffer_close.argtypes = [C.c_void_p, C.c_int]
+        L.cris_peer_allreduce_f32.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_double, C.c_void_p]
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_T[ch] for ch in sig]
@@ -112,7 +118,9 @@ def lib():
 def exported_symbols():
     """Every entry point include/cris_b200.h declares (used by the CPU 'library loads' test)."""
     return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
-            "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset", *_SIGS.keys()]
+            "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset",
+            "cris_peer_buffer_bytes", "cris_peer_buffer_create", "cris_peer_buffer_open", "cris_peer_buffer_close",
+            "cris_peer_allreduce_f32", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

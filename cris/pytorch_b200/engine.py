@@ -26,6 +26,7 @@ from ._lib import GemmArgs, call, gemm
 ACT_NONE, ACT_RELU, ACT_QGELU = 0, 1, 2
 TAP_NONE, TAP_ACCUM, TAP_WGRAD = 0, 1, 2
 BN_EPS, LN_EPS, BN_MOMENTUM = 1e-5, 1e-5, 0.1
+PEER_SLOT_FLOATS, PEER_MAX_SLOTS = 4096, 1024  # CRIS_PEER_* in include/cris_b200.h
 
 
 def _r8(x: int) -> int:
@@ -171,6 +172,19 @@ class Engine:
             dropout_p = 0.0
         return cls(_NoModel())
 
+    def needs_sync_bn(self) -> bool:
+        """Training statistics are shared across ranks iff the model was converted to SyncBatchNorm (train.py:97-98)."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        return self.force_sync_bn or any(isinstance(m, nn.SyncBatchNorm) for m in self.model.modules())
+
+    def peer_exchange(self, device):
+        """NVLink peer-memory exchange (collective on first call), or None -> torch.distributed.all_reduce."""
+        if device.type != "cuda":
+            return None
+        from . import peer
+        return peer.get_exchange(device)
+
     def step_counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != device:
             self._counter = torch.zeros(1, dtype=torch.int64, device=device)
@@ -197,8 +211,10 @@ class Engine:
                     continue
                 names.append(k)
                 params.append(p)
-            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-            graphs_ok = self.use_graphs and (not multi or os.environ.get("CRIS_B200_GRAPHS_DDP", "0") == "1")
+            # cross-rank BatchNorm statistics inside a captured graph need the NVLink peer exchange (csrc/peer.cu):
+            # a NCCL call cannot be replayed from the forward/backward graphs
+            graphs_ok = self.use_graphs and (not self.needs_sync_bn() or self.peer_exchange(img.device) is not None
+                                             or os.environ.get("CRIS_B200_GRAPHS_DDP", "0") == "1")
             if graphs_ok and self.debug_taps is None and self.probe_name is None:
                 key = (tuple(img.shape), tuple(word.shape), tuple(mask.shape), img.device.index, float(model.dropout_p))
                 gs = self.graphs.get(key)
@@ -343,8 +359,9 @@ class Run:
         self.n_seed = 0
         self.seed_dev = engine.step_counter(self.dev).data_ptr()
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        self.sync_bn = training and self.world > 1 and (engine.force_sync_bn or any(
-            isinstance(m, nn.SyncBatchNorm) for m in self.model.modules()))
+        self.sync_bn = training and engine.needs_sync_bn()
+        self.xchg = engine.peer_exchange(self.dev) if self.sync_bn else None
+        self.xslot = 0  # exchange site index inside this pass (forward sites, then backward sites)
 
     # ---- small helpers -------------------------------------------------------------------------
     def new(self, rows, C, fp32=False, geom=None, zero=False, ld=None) -> Mat:
@@ -489,7 +506,15 @@ class Run:
 
     # ---- BatchNorm ---------------------------------------------------------------------------------
     def allreduce(self, t: torch.Tensor):
-        dist.all_reduce(t)
+        """Sum the statistics vector over ranks: one peer-memory kernel on NVLink, else torch.distributed."""
+        if self.xchg is not None and t.numel() <= PEER_SLOT_FLOATS and self.xslot < PEER_MAX_SLOTS:
+            self.xchg.allreduce(self.xslot, t)
+            self.xslot += 1
+        else:
+            if t.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("cross-rank BatchNorm statistics fell back to NCCL inside a CUDA-graph capture "
+                                   f"(exchange site {self.xslot}, {t.numel()} floats)")
+            dist.all_reduce(t)
 
     def bn_forward(self, z: Mat, prefix: str, relu: bool, resid: Optional[Mat] = None, out: Optional[Mat] = None,
                    partials=None, n_tiles=0) -> Mat:

@@ -210,6 +210,25 @@ int cris_dynconv_bce_bwd(const void* x, int64_t ldx, const float* t, int64_t ldt
                          const float* target, const float* g, float* dl, void* dx, int64_t lddx, float* dt,
                          int64_t lddt, int B, int H, int W, int C, void* stream);
 
+/* ---- cross-GPU statistics exchange over NVLink peer memory (the collective inside torch.nn.SyncBatchNorm,
+ *      train.py:97-98: forward all-gather of batch statistics, backward all-reduce of sum_dy / sum_dy_xmu).
+ *      Each rank creates ONE buffer, ships its 64-byte CUDA-IPC handle to the other ranks of the node (any side
+ *      channel; the Python surface uses torch.distributed's object all-gather), opens the peers' handles, and then
+ *      cris_peer_allreduce_f32 sums an fp32 vector across ranks in ONE kernel (flag handshake + peer loads),
+ *      CUDA-graph replayable.  `slot` identifies the exchange site: every rank must issue the same slot sequence. */
+#define CRIS_PEER_MAX_WORLD 8
+#define CRIS_PEER_MAX_SLOTS 1024
+#define CRIS_PEER_SLOT_FLOATS 4096
+#define CRIS_PEER_HANDLE_BYTES 64
+size_t cris_peer_buffer_bytes(void);
+int cris_peer_buffer_create(void** dev_ptr, unsigned char* handle_out /* [CRIS_PEER_HANDLE_BYTES] */);
+int cris_peer_buffer_open(const unsigned char* handle, void** dev_ptr);
+int cris_peer_buffer_close(void* dev_ptr, int owned);
+/* peer_ptrs: HOST array of `world` device pointers (index = rank; entry `rank` is the own buffer).  out may alias in.
+ * timeout_s <= 0 -> 120 s; a peer that never arrives makes the kernel print and trap instead of hanging. */
+int cris_peer_allreduce_f32(void* const* peer_ptrs, int world, int rank, int slot, const float* in, float* out, int n,
+                            double timeout_s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
