@@ -52,7 +52,7 @@ _SIGS = {
     "cris_bn_apply": "pqpppqpqqiiiip",
     "cris_bn_bwd_apply": "pqpqpqpppppdpqpqiqiiiip",
     "cris_layernorm_fwd": "piqpppqipiqpqppqifp",
-    "cris_layernorm_bwd": "piqpqpiqppppiqiqip",
+    "cris_layernorm_bwd": "piqpqpiqppppiqippqip",
     "cris_avgpool2_fwd": "pqpqiiiip",
     "cris_avgpool2_bwd": "pqpqiiiiip",
     "cris_upsample2x_fwd": "pqpqiiiip",

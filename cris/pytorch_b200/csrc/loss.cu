@@ -8,44 +8,68 @@
 
 namespace cris {
 
-// t[b, c*9 + tap] (fp32, pitch ldt) -> smem k[tap][c]; bias = t[b, C*9]
+// t[b, c*9 + tap] (fp32, pitch ldt) -> smem k[(tap*8 + j)*G + g] for channel c = 8g + j (G = C/8): lane g of a
+// warp reads consecutive words (no bank conflicts); bias = t[b, C*9]
 __device__ __forceinline__ void stage_kernel(const float* __restrict__ t, long long ldt, int b, int C, float* sk) {
+  const int G = C / 8;
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
     const int c = i / 9, tap = i - c * 9;
-    sk[tap * C + c] = t[(long long)b * ldt + i];
+    sk[(tap * 8 + (c & 7)) * G + (c >> 3)] = t[(long long)b * ldt + i];
   }
 }
 
+constexpr int kDynPix = 128;  // consecutive output pixels per block (their 3x3 windows overlap in L1)
+
+// One warp per output pixel, lane = channel group of 8 (G <= 32: the lane's 72 kernel weights live in registers).
+template <bool REGS>
 __global__ void __launch_bounds__(256)
     dynconv_bce_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ t,
                            long long ldt, const float* __restrict__ mask, int Hm, int Wm, float* __restrict__ pred,
                            float* __restrict__ mask_out, float* __restrict__ loss_sum, int B, int H, int W, int C,
                            float inv_n) {
-  extern __shared__ float sk[];  // [9][C]
+  extern __shared__ float sk[];  // [9][8][G]
   __shared__ float s_loss[8];
   const int b = blockIdx.y;
   stage_kernel(t, ldt, b, C, sk);
   __syncthreads();
   const float bias = t[(long long)b * ldt + 9 * C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wp = W + 2;
+  const int wp = W + 2, G = C / 8;
   const int sh = mask ? Hm / H : 1, sw = mask ? Wm / W : 1;
+  float kr[REGS ? 72 : 1];
+  if (REGS) {
+#pragma unroll
+    for (int i = 0; i < 72; ++i) kr[i] = lane < G ? sk[i * G + lane] : 0.f;
+  }
   float lsum = 0.f;
   const int npix = H * W;
-  for (int p = blockIdx.x * 8 + warp; p < npix; p += gridDim.x * 8) {
+  const int p1 = min(npix, (blockIdx.x + 1) * kDynPix);
+  for (int p = blockIdx.x * kDynPix + warp; p < p1; p += 8) {
     const int h = p / W, w = p - h * W;
+    const __nv_bfloat16* xb = x + (((long long)b * (H + 2) + h) * wp + w) * ldx;
     float acc = 0.f;
-    for (int g = lane; g < C / 8; g += 32) {
+    if (REGS) {
+      if (lane < G) {
+        float v[9][8];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
+          for (int kx = 0; kx < 3; ++kx) ld8(xb + ((long long)ky * wp + kx) * ldx + lane * 8, v[ky * 3 + kx]);
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fmaf(v[tp][k], kr[tp * 8 + k], acc);
+      }
+    } else {
+      for (int g = lane; g < G; g += 32) {
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
           float v[8];
-          ld8(x + (((long long)b * (H + 2) + h + ky) * wp + w + kx) * ldx + g * 8, v);
-          const float* kk = sk + (ky * 3 + kx) * C + g * 8;
+          ld8(xb + ((long long)(tp / 3) * wp + (tp % 3)) * ldx + g * 8, v);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc = fmaf(v[k], kk[k], acc);
+          for (int k = 0; k < 8; ++k) acc = fmaf(v[k], sk[(tp * 8 + k) * G + g], acc);
         }
+      }
     }
     acc = warp_sum(acc) + bias;
     if (lane == 0) {
@@ -94,6 +118,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // dX[b, h+1, w+1, c] = sum_tap dl[b, h-(ky-1), w-(kx-1)] * k[tap][c]; zero border
+template <bool REGS>
 __global__ void __launch_bounds__(256)
     dynconv_bwd_x_kernel(const float* __restrict__ dl, const float* __restrict__ t, long long ldt,
                          __nv_bfloat16* __restrict__ dx, long long lddx, int B, int H, int W, int C) {
@@ -102,8 +127,14 @@ __global__ void __launch_bounds__(256)
   stage_kernel(t, ldt, b, C, sk);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hp = H + 2, wp = W + 2;
-  for (int r = blockIdx.x * 8 + warp; r < hp * wp; r += gridDim.x * 8) {
+  const int hp = H + 2, wp = W + 2, G = C / 8;
+  float kr[REGS ? 72 : 1];
+  if (REGS) {
+#pragma unroll
+    for (int i = 0; i < 72; ++i) kr[i] = lane < G ? sk[i * G + lane] : 0.f;
+  }
+  const int r1 = min(hp * wp, (blockIdx.x + 1) * kDynPix);
+  for (int r = blockIdx.x * kDynPix + warp; r < r1; r += 8) {
     const int hq = r / wp, wq = r - hq * wp;
     const bool interior = hq >= 1 && hq <= H && wq >= 1 && wq <= W;
     float d[9];
@@ -115,15 +146,25 @@ __global__ void __launch_bounds__(256)
         d[ky * 3 + kx] = (interior && hl >= 0 && hl < H && wl >= 0 && wl < W)
                              ? dl[((long long)b * H + hl) * W + wl] : 0.f;
       }
-    for (int g = lane; g < C / 8; g += 32) {
-      float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __nv_bfloat16* out = dx + ((long long)b * hp * wp + r) * lddx;
+    if (REGS) {
+      if (lane < G) {
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) {
-        const float* kk = sk + tp * C + g * 8;
+        for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(d[tp], kk[k], o[k]);
+          for (int k = 0; k < 8; ++k) o[k] = fmaf(d[tp], kr[tp * 8 + k], o[k]);
+        st8(out + lane * 8, o);
       }
-      st8(dx + ((long long)b * hp * wp + r) * lddx + g * 8, o);
+    } else {
+      for (int g = lane; g < G; g += 32) {
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaf(d[tp], sk[(tp * 8 + k) * G + g], o[k]);
+        st8(out + g * 8, o);
+      }
     }
   }
 }
@@ -180,14 +221,19 @@ int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt
   CRIS_CHECK_ARG(mask == nullptr || (Hm % H == 0 && Wm % W == 0), "dynconv: mask %dx%d not an integer multiple", Hm, Wm);
   static bool attr = false;
   if (!attr) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  dim3 grid(max(1, min((H * W + 7) / 8, 148 * 8 / max(B, 1) + 1)), B);
-  dynconv_bce_fwd_kernel<<<grid, 256, 9 * C * 4, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, t, ldt,
-                                                          mask, Hm, Wm, pred, mask_out, loss_sum, B, H, W, C,
-                                                          1.f / ((float)B * H * W));
+  dim3 grid((H * W + kDynPix - 1) / kDynPix, B);
+  const float inv_n = 1.f / ((float)B * H * W);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (C <= 256)
+    dynconv_bce_fwd_kernel<true><<<grid, 256, 9 * C * 4, STREAM>>>(xb, ldx, t, ldt, mask, Hm, Wm, pred, mask_out,
+                                                                  loss_sum, B, H, W, C, inv_n);
+  else
+    dynconv_bce_fwd_kernel<false><<<grid, 256, 9 * C * 4, STREAM>>>(xb, ldx, t, ldt, mask, Hm, Wm, pred, mask_out,
+                                                                   loss_sum, B, H, W, C, inv_n);
   CRIS_LAUNCH_OK();
   return 0;
 }
@@ -200,16 +246,21 @@ int cris_dynconv_bce_bwd(const void* x, int64_t ldx, const float* t, int64_t ldt
   CRIS_CHECK_ARG(C % 8 == 0 && 9 * C * 4 <= 96 * 1024, "dynconv: C=%d unsupported", C);
   static bool attr = false;
   if (!attr) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
   const int npix = H * W;
   const float inv_n = 1.f / ((float)B * npix);
   bce_dlogit_kernel<<<dim3((npix + 255) / 256, B), 256, 0, STREAM>>>(pred, target, g, dl, dt, lddt, npix, C, inv_n);
   CRIS_LAUNCH_OK();
-  dim3 gx(max(1, min(((H + 2) * (W + 2) + 7) / 8, 148 * 8 / max(B, 1) + 1)), B);
-  dynconv_bwd_x_kernel<<<gx, 256, 9 * C * 4, STREAM>>>(dl, t, ldt, reinterpret_cast<__nv_bfloat16*>(dx), lddx, B, H, W,
-                                                      C);
+  dim3 gx(((H + 2) * (W + 2) + kDynPix - 1) / kDynPix, B);
+  if (C <= 256)
+    dynconv_bwd_x_kernel<true><<<gx, 256, 9 * C * 4, STREAM>>>(dl, t, ldt, reinterpret_cast<__nv_bfloat16*>(dx), lddx, B,
+                                                              H, W, C);
+  else
+    dynconv_bwd_x_kernel<false><<<gx, 256, 9 * C * 4, STREAM>>>(dl, t, ldt, reinterpret_cast<__nv_bfloat16*>(dx), lddx, B,
+                                                               H, W, C);
   CRIS_LAUNCH_OK();
   const int rpb = 4;
   dim3 gk((H + rpb - 1) / rpb, B);

@@ -2,12 +2,14 @@
 // Reference call sites: nn.BatchNorm2d/1d + SyncBatchNorm (model/clip.py:18-26,171-183;
 // model/layers.py:8-16,262; train.py:97-98), nn.LayerNorm (model/clip.py:226-231,
 // model/layers.py:199-216).  All HBM-bound: 16-byte vector accesses, one pass per tensor.
+#include <algorithm>
+
 #include "vec.cuh"
 
 namespace cris {
 
 // ---------------------------------------------------------------------------------------------
-// column reductions over a [rows, C] matrix -> partials[block][2][C]
+// column reductions over a [rows, C] matrix -> partials[block % 64][2][C] (atomic accumulation)
 //   MODE 0: (x, x^2)                        batch statistics of a tensor not produced by the GEMM
 //   MODE 1: (dz, dz*xhat), dz = dy*(y>0)    BatchNorm backward
 //   MODE 2: (dy, -)                         bias gradient
@@ -112,9 +114,15 @@ __global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs 
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += sm[o + i]; s1[i] += sm[o + 8 + i]; }
       }
-      float* dst = p.partials + (size_t)blockIdx.x * 2 * p.C;
-      st8f(dst + c, s0);
-      st8f(dst + p.C + c, s1);
+      // 64 partial rows shared by all blocks (vector fp32 atomics into a caller-zeroed buffer): the finalize
+      // kernels read 64 rows instead of one row per block
+      float* dst = p.partials + (size_t)(blockIdx.x & 63) * 2 * p.C;
+      atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(s0[0], s0[1], s0[2], s0[3]));
+      atomicAdd(reinterpret_cast<float4*>(dst + c + 4), make_float4(s0[4], s0[5], s0[6], s0[7]));
+      if (MODE != 2) {
+        atomicAdd(reinterpret_cast<float4*>(dst + p.C + c), make_float4(s1[0], s1[1], s1[2], s1[3]));
+        atomicAdd(reinterpret_cast<float4*>(dst + p.C + c + 4), make_float4(s1[4], s1[5], s1[6], s1[7]));
+      }
     }
   }
 }
@@ -332,59 +340,200 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = (dy + dy2)*gamma
+// dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = (dy + dy2)*gamma; the parameter gradients
+// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy ride along in registers (each lane owns fixed columns) and are
+// flushed once per block: shared-memory reduction over the 8 warps, then one fp32 atomic per column.
 template <int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     layernorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, long long lddy,
                          const __nv_bfloat16* __restrict__ dy2, long long lddy2, const void* __restrict__ x,
                          int x_fp32, long long ldx, const float* __restrict__ gamma, const float* __restrict__ mean,
                          const float* __restrict__ rstd, void* __restrict__ dx, int dx_fp32, long long lddx,
-                         int dx_accumulate, long long rows, int C) {
+                         int dx_accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
+                         int C) {
+  __shared__ float red[2 * MAXV * 128];
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int nv = C / 128;
-  const float mu = mean[row], rs = rstd[row];
-  float g[MAXV][4], xh[MAXV][4];
-  float sg = 0.f, sgx = 0.f;
+  float dg[MAXV][4], db[MAXV][4];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      float d[4], xv[4];
-      ld4x(dy, row * lddy + c, dy_fp32, d);
-      if (dy2 != nullptr) {
-        float d2[4];
-        ld4x(dy2, row * lddy2 + c, 0, d2);
-        d[0] += d2[0]; d[1] += d2[1]; d[2] += d2[2]; d[3] += d2[3];
-      }
-      ld4x(x, row * ldx + c, x_fp32, xv);
-      const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
-      const float gg[4] = {ga.x, ga.y, ga.z, ga.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        xh[i][k] = (xv[k] - mu) * rs;
-        g[i][k] = d[k] * gg[k];
-        sg += g[i][k];
-        sgx += g[i][k] * xh[i][k];
+    for (int k = 0; k < 4; ++k) dg[i][k] = db[i][k] = 0.f;
+  }
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[MAXV][4], xh[MAXV][4];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        float d[4], xv[4];
+        ld4x(dy, row * lddy + c, dy_fp32, d);
+        if (dy2 != nullptr) {
+          float d2[4];
+          ld4x(dy2, row * lddy2 + c, 0, d2);
+          d[0] += d2[0]; d[1] += d2[1]; d[2] += d2[2]; d[3] += d2[3];
+        }
+        ld4x(x, row * ldx + c, x_fp32, xv);
+        const float4 gv = *reinterpret_cast<const float4*>(gamma + c);  // L1-resident
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xh[i][k] = (xv[k] - mu) * rs;
+          g[i][k] = d[k] * ga[k];
+          sg += g[i][k];
+          sgx += g[i][k] * xh[i][k];
+          db[i][k] += d[k];
+          dg[i][k] = fmaf(d[k], xh[i][k], dg[i][k]);
+        }
+      }
+    }
+    if (dx == nullptr) continue;
+    const float mg = warp_sum(sg) / C, mgx = warp_sum(sgx) / C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < nv) {
+        const int c = i * 128 + lane * 4;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rs * (g[i][k] - mg - xh[i][k] * mgx);
+        if (dx_accumulate) {
+          float old[4];
+          ld4x(dx, row * lddx + c, dx_fp32, old);
+          o[0] += old[0]; o[1] += old[1]; o[2] += old[2]; o[3] += old[3];
+        }
+        st4x(dx, row * lddx + c, dx_fp32, o);
       }
     }
   }
-  const float mg = warp_sum(sg) / C, mgx = warp_sum(sgx) / C;
+  if (dgamma == nullptr) return;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      float o[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = rs * (g[i][k] - mg - xh[i][k] * mgx);
-      if (dx_accumulate) {
-        float old[4];
-        ld4x(dx, row * lddx + c, dx_fp32, old);
-        o[0] += old[0]; o[1] += old[1]; o[2] += old[2]; o[3] += old[3];
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&red[i * 128 + lane * 4 + k], dg[i][k]);
+        atomicAdd(&red[C + i * 128 + lane * 4 + k], db[i][k]);
       }
-      st4x(dx, row * lddx + c, dx_fp32, o);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[C + i]);
+  }
+}
+
+// ---- wide rows (C > 512, C % 256 == 0): one block of C/8 threads per row, 8 contiguous columns per thread ----
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* sm) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // the previous round's readers are done with sm
+  if (lane == 0) sm[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = lane < nw ? sm[lane] : make_float2(0.f, 0.f);
+  t.x = warp_sum(t.x);
+  t.y = warp_sum(t.y);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+    layernorm_fwd_wide_kernel(const void* __restrict__ x, int x_fp32, long long ldx, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ add, long long ldadd,
+                              int add_period, void* __restrict__ y, int y_fp32, long long ldy,
+                              __nv_bfloat16* __restrict__ y2, long long ldy2, float* __restrict__ mean_out,
+                              float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  __shared__ float2 sm[32];
+  const int c = threadIdx.x * 8;
+  float ga[8], be[8];
+  ld8f(gamma + c, ga);
+  ld8f(beta + c, be);
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    float v[8];
+    ld8x(x, row * ldx + c, x_fp32, v);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    const float mean = block_sum2(s, 0.f, sm).x / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q += d * d; }
+    const float rstd = rsqrtf(block_sum2(q, 0.f, sm).x / C + eps);
+    if (threadIdx.x == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (v[k] - mean) * rstd * ga[k] + be[k];
+    if (y != nullptr) st8x(y, row * ldy + c, y_fp32, o);
+    if (y2 != nullptr) {
+      float a[8];
+      ld8f(add + (row % add_period) * ldadd + c, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += a[k];
+      st8(y2 + row * ldy2 + c, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_wide_kernel(const void* __restrict__ dy, int dy_fp32, long long lddy,
+                              const __nv_bfloat16* __restrict__ dy2, long long lddy2, const void* __restrict__ x,
+                              int x_fp32, long long ldx, const float* __restrict__ gamma,
+                              const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx,
+                              int dx_fp32, long long lddx, int dx_accumulate, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, long long rows, int C) {
+  __shared__ float2 sm[32];
+  const int c = threadIdx.x * 8;
+  float ga[8], dg[8], db[8];
+  ld8f(gamma + c, ga);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dg[k] = db[k] = 0.f;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mu = mean[row], rs = rstd[row];
+    float d[8], xh[8], g[8];
+    ld8x(dy, row * lddy + c, dy_fp32, d);
+    if (dy2 != nullptr) {
+      float d2[8];
+      ld8(dy2 + row * lddy2 + c, d2);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += d2[k];
+    }
+    ld8x(x, row * ldx + c, x_fp32, xh);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      xh[k] = (xh[k] - mu) * rs;
+      g[k] = d[k] * ga[k];
+      sg += g[k];
+      sgx += g[k] * xh[k];
+      db[k] += d[k];
+      dg[k] = fmaf(d[k], xh[k], dg[k]);
+    }
+    if (dx == nullptr) continue;
+    const float2 t = block_sum2(sg, sgx, sm);
+    const float mg = t.x / C, mgx = t.y / C;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = rs * (g[k] - mg - xh[k] * mgx);
+    if (dx_accumulate) {
+      float old[8];
+      ld8x(dx, row * lddx + c, dx_fp32, old);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += old[k];
+    }
+    st8x(dx, row * lddx + c, dx_fp32, o);
+  }
+  if (dgamma == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(dgamma + c + k, dg[k]);
+    atomicAdd(dbeta + c + k, db[k]);
   }
 }
 
@@ -543,34 +692,38 @@ int cris_layernorm_fwd(const void* x, int x_fp32, int64_t ldx, const float* gamm
                        int64_t ldadd, int add_period, void* y, int y_fp32, int64_t ldy, void* y2, int64_t ldy2,
                        float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
   CRIS_CHECK_ARG(C % 128 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 128 and <= 2048", C);
-  const int grid = (int)((rows + 7) / 8);
+  CRIS_CHECK_ARG(C <= 512 || C % 256 == 0, "layernorm: C=%d > 512 must be a multiple of 256", C);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int period = add_period > 0 ? add_period : 1;
   if (C <= 512)
-    layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, x_fp32, ldx, gamma, beta, add, ldadd, add_period > 0 ? add_period : 1,
-                                                 y, y_fp32, ldy, reinterpret_cast<__nv_bfloat16*>(y2), ldy2, mean, rstd,
-                                                 rows, C, eps);
+    layernorm_fwd_kernel<4><<<(int)((rows + 7) / 8), 256, 0, s>>>(x, x_fp32, ldx, gamma, beta, add, ldadd, period, y,
+                                                                  y_fp32, ldy, reinterpret_cast<__nv_bfloat16*>(y2),
+                                                                  ldy2, mean, rstd, rows, C, eps);
   else
-    layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_fp32, ldx, gamma, beta, add, ldadd,
-                                                  add_period > 0 ? add_period : 1, y, y_fp32, ldy,
-                                                  reinterpret_cast<__nv_bfloat16*>(y2), ldy2, mean, rstd, rows, C, eps);
+    layernorm_fwd_wide_kernel<<<(int)std::min<int64_t>(rows, 148 * 8), C / 8, 0, s>>>(
+        x, x_fp32, ldx, gamma, beta, add, ldadd, period, y, y_fp32, ldy, reinterpret_cast<__nv_bfloat16*>(y2), ldy2,
+        mean, rstd, rows, C, eps);
   CRIS_LAUNCH_OK();
   return 0;
 }
 
 int cris_layernorm_bwd(const void* dy, int dy_fp32, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
                        int x_fp32, int64_t ldx, const float* gamma, const float* mean, const float* rstd, void* dx,
-                       int dx_fp32, int64_t lddx, int dx_accumulate, int64_t rows, int C, void* stream) {
+                       int dx_fp32, int64_t lddx, int dx_accumulate, float* dgamma, float* dbeta, int64_t rows, int C,
+                       void* stream) {
   CRIS_CHECK_ARG(C % 128 == 0 && C <= 2048, "layernorm: C=%d must be a multiple of 128 and <= 2048", C);
-  const int grid = (int)((rows + 7) / 8);
+  CRIS_CHECK_ARG(C <= 512 || C % 256 == 0, "layernorm: C=%d > 512 must be a multiple of 256", C);
+  CRIS_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
+  CRIS_CHECK_ARG(dx != nullptr || dgamma != nullptr, "layernorm_bwd: nothing to compute");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (C <= 512)
-    layernorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2,
-                                                 x, x_fp32, ldx, gamma, mean, rstd, dx, dx_fp32, lddx, dx_accumulate,
-                                                 rows, C);
+    layernorm_bwd_kernel<4><<<(int)std::min<int64_t>((rows + 7) / 8, 148 * 2), 256, 0, s>>>(
+        dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2, x, x_fp32, ldx, gamma, mean, rstd, dx,
+        dx_fp32, lddx, dx_accumulate, dgamma, dbeta, rows, C);
   else
-    layernorm_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2,
-                                                  x, x_fp32, ldx, gamma, mean, rstd, dx, dx_fp32, lddx, dx_accumulate,
-                                                  rows, C);
+    layernorm_bwd_wide_kernel<<<(int)std::min<int64_t>(rows, 148 * 8), C / 8, 0, s>>>(
+        dy, dy_fp32, lddy, reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2, x, x_fp32, ldx, gamma, mean, rstd, dx,
+        dx_fp32, lddx, dx_accumulate, dgamma, dbeta, rows, C);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -337,6 +337,11 @@ class _GraphFunction(torch.autograd.Function):
 
 class Run:
     """State of one forward (+ backward) pass."""
+    # defaults for helpers that tests build without __init__
+    xchg = None
+    xslot = 0
+    _zarena: Optional[torch.Tensor] = None
+    _zoff = 0
 
     def __init__(self, engine: Engine, img, word, mask, training: bool, record: bool):
         self.e = engine
@@ -362,6 +367,8 @@ class Run:
         self.sync_bn = training and engine.needs_sync_bn()
         self.xchg = engine.peer_exchange(self.dev) if self.sync_bn else None
         self.xslot = 0  # exchange site index inside this pass (forward sites, then backward sites)
+        self._zarena: Optional[torch.Tensor] = None
+        self._zoff = 0
 
     # ---- small helpers -------------------------------------------------------------------------
     def new(self, rows, C, fp32=False, geom=None, zero=False, ld=None) -> Mat:
@@ -374,7 +381,19 @@ class Run:
         return self.new(N * (H + 2) * (W + 2), C, False, (N, H, W), zero, ld)
 
     def f32(self, n, zero=False):
-        return (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.dev)
+        if zero:
+            return self.zeros_f32(n)
+        return torch.empty(n, dtype=torch.float32, device=self.dev)
+
+    def zeros_f32(self, n):
+        """n zero floats carved from a shared pre-zeroed arena (one memset per 4M floats instead of one per use)."""
+        n_al = (n + 63) // 64 * 64
+        if self._zarena is None or self._zoff + n_al > self._zarena.numel():
+            self._zarena = torch.zeros(max(n_al, 1 << 22), dtype=torch.float32, device=self.dev)
+            self._zoff = 0
+        t = self._zarena[self._zoff:self._zoff + n]
+        self._zoff += n_al
+        return t
 
     def tap(self, name: str, m: Mat):
         if self.e.debug_taps is not None:
@@ -496,11 +515,11 @@ class Run:
         nb = max(1, min(592, m.rows // 64))
         for c0 in range(0, wpad, 2048):
             cw = min(2048, wpad - c0)
-            pt = self.f32(nb * 2 * cw)
+            pt = self.zeros_f32(min(nb, 64) * 2 * cw)
             call("cris_col_reduce", 2, m.ptr + c0 * m.esize, m.ld, int(m.fp32), None, 0, None, 0, None, 0, 0, None, None,
                  None, None, m.rows, cw, 0, hp, wp, pt.data_ptr(), nb)
             sm = self.f32(2 * cw)
-            call("cris_bn_reduce_partials", pt.data_ptr(), nb, cw, sm.data_ptr())
+            call("cris_bn_reduce_partials", pt.data_ptr(), min(nb, 64), cw, sm.data_ptr())
             out[c0:c0 + cw].copy_(sm[:cw])
         return out
 
@@ -530,10 +549,11 @@ class Run:
         sums = None
         if self.training:
             if partials is None:
-                n_tiles = max(1, min(592, z.rows // 64))
-                partials = self.f32(n_tiles * 2 * C)
+                nb = max(1, min(592, z.rows // 64))
+                n_tiles = min(nb, 64)
+                partials = self.zeros_f32(n_tiles * 2 * C)
                 call("cris_col_reduce", 0, z.ptr, z.ld, 0, None, 0, None, 0, None, 0, 0, None, None, None, None, z.rows,
-                     C, 0, z.hp, z.wp, partials.data_ptr(), n_tiles)
+                     C, 0, z.hp, z.wp, partials.data_ptr(), nb)
             sums = self.f32(2 * C)
             if self.sync_bn:
                 call("cris_bn_reduce_partials", partials.data_ptr(), n_tiles, C, sums.data_ptr())
@@ -561,7 +581,7 @@ class Run:
             if dy is None:
                 return
             nb = max(1, min(592, z.rows // 64))
-            part = self.f32(nb * 2 * C)
+            part = self.zeros_f32(min(nb, 64) * 2 * C)
             # without a residual the ReLU mask is recomputed from z (x*scale+shift > 0): y is not re-read
             ymask = y if (resid is not None or not relu) else None
             call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, ymask.ptr if ymask else None, ymask.ld if ymask else 0,
@@ -570,7 +590,7 @@ class Run:
             bs = self.f32(2 * C)
             # parameter gradients are LOCAL sums (DDP averages them), dx needs the GLOBAL sums
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
-            call("cris_stats_finalize_bwd", part.data_ptr(), nb, C, bs.data_ptr(), gb.data_ptr(), gg.data_ptr())
+            call("cris_stats_finalize_bwd", part.data_ptr(), min(nb, 64), C, bs.data_ptr(), gb.data_ptr(), gg.data_ptr())
             if self.sync_bn:
                 self.allreduce(bs)
             dz = self.new(z.rows, C, False, z.geom)
@@ -760,18 +780,13 @@ class Run:
                 return
             if d1 is None:
                 d1, d2 = d2, None
-            nb = max(1, min(592, x.rows // 64))
-            pt = self.f32(nb * 2 * C)
-            call("cris_col_reduce", 3, d1.ptr, d1.ld, int(d1.fp32), d2.ptr if d2 else None, d2.ld if d2 else 0, None, 0,
-                 x.ptr, x.ld, int(x.fp32), stats.data_ptr(), stats.data_ptr() + 4 * x.rows, None, None, x.rows, C, 0, 0, 0,
-                 pt.data_ptr(), nb)
+            # one pass: dx and the gamma/beta gradients (accumulated into the zero-filled parameter-gradient buffer)
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
-            call("cris_stats_finalize_bwd", pt.data_ptr(), nb, C, None, gb.data_ptr(), gg.data_ptr())
-            if x.need_grad:
-                slot, acc = self.grad_slot(x)
-                call("cris_layernorm_bwd", d1.ptr, int(d1.fp32), d1.ld, d2.ptr if d2 else None, d2.ld if d2 else 0,
-                     x.ptr, int(x.fp32), x.ld, gamma.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * x.rows,
-                     slot.ptr, int(slot.fp32), slot.ld, int(acc), x.rows, C)
+            slot, acc = self.grad_slot(x) if x.need_grad else (None, False)
+            call("cris_layernorm_bwd", d1.ptr, int(d1.fp32), d1.ld, d2.ptr if d2 else None, d2.ld if d2 else 0,
+                 x.ptr, int(x.fp32), x.ld, gamma.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * x.rows,
+                 slot.ptr if slot else None, int(slot.fp32) if slot else 0, slot.ld if slot else 0, int(acc),
+                 gg.data_ptr(), gb.data_ptr(), x.rows, C)
 
         if self.training:
             self.on_backward(bwd)

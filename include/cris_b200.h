@@ -102,7 +102,8 @@ int cris_gemm_args_last_offset(void);  /* offsetof(cris_gemm_args, d_col_stride)
 
 /* ---- column reductions / BatchNorm ------------------------------------------------------ */
 /*
- * Column reduction of a [rows, C] matrix into partials[n_blocks][2][C] (fp32):
+ * Column reduction of a [rows, C] matrix, ACCUMULATED (fp32 atomics) into partials[min(n_blocks, 64)][2][C], which the
+ * caller zero-fills; block i adds into row i % 64 (the finalize kernels below then read at most 64 rows):
  *   mode 0: (sum x, sum x^2)                       batch statistics (nn.BatchNorm2d training,
  *                                                  model/clip.py:18-26,171-183; model/layers.py:8-16,262)
  *   mode 1: (sum dz, sum dz*xhat), dz = dy*(y>0)   BatchNorm backward (batch_norm_backward_reduce); with y == NULL the
@@ -145,9 +146,12 @@ int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, 
 int cris_layernorm_fwd(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, const float* add,
                        int64_t ldadd, int add_period, void* y, int y_fp32, int64_t ldy, void* y2, int64_t ldy2,
                        float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+/* dx (+)= LN backward of (dy + dy2); dgamma/dbeta (fp32, caller-zeroed or running totals) are ACCUMULATED with
+ * atomics in the same pass (NULL pair = skip); dx == NULL computes the parameter gradients only */
 int cris_layernorm_bwd(const void* dy, int dy_fp32, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
                        int x_fp32, int64_t ldx, const float* gamma, const float* mean, const float* rstd, void* dx,
-                       int dx_fp32, int64_t lddx, int dx_accumulate, int64_t rows, int C, void* stream);
+                       int dx_fp32, int64_t lddx, int dx_accumulate, float* dgamma, float* dbeta, int64_t rows, int C,
+                       void* stream);
 
 /* ---- spatial ops on padded NHWC (nn.AvgPool2d clip.py:23,35,184; F.interpolate bilinear layers.py:54-56,293,304;
  *      f5*state layers.py:290; reshape/permute glue clip.py:113-118,140, layers.py:166,179; CoordConv

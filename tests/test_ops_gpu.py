@@ -192,10 +192,12 @@ def test_linear(act, transposed, n_out):
         assert rel(run.pgrad["b"].cpu(), br.grad) < 1e-2
 
 
-@pytest.mark.parametrize("C,x_fp32,with_add", [(512, True, True), (128, False, False), (2048, False, False)])
-def test_layernorm(C, x_fp32, with_add):
+@pytest.mark.parametrize("C,x_fp32,with_add,rows", [(512, True, True, 130), (128, False, False, 130),
+                                                     (2048, False, False, 130), (512, False, True, 5200),
+                                                     (2048, True, False, 2600), (1024, False, False, 77)])
+def test_layernorm(C, x_fp32, with_add, rows):
     g = torch.Generator().manual_seed(C)
-    rows, period = 130, 26
+    period = 26
     x = torch.randn(rows, C, generator=g) * 2 + 0.5
     if not x_fp32:
         x = _bf(x)
@@ -283,11 +285,11 @@ def test_avgpool_upsample():
     assert rel(out_t(run.grad_of(xm)), xr.grad) < 1e-2
 
 
-def test_dynconv_bce():
+@pytest.mark.parametrize("B,C,H,W", [(3, 64, 12, 10), (2, 256, 26, 26), (2, 320, 9, 15)])
+def test_dynconv_bce(B, C, H, W):
     from cris.pytorch_b200.engine import Mat
     from cris.pytorch_b200._lib import call
     g = torch.Generator().manual_seed(9)
-    B, C, H, W = 3, 64, 12, 10
     x = _bf(torch.randn(B, C, H, W, generator=g))
     t = torch.randn(B, 9 * C + 1, generator=g) * 0.05
     mask = torch.rand(B, 1, 4 * H, 4 * W, generator=g)

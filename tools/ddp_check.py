@@ -58,9 +58,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arch", default="r50")
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--size", type=int, default=0, help="default: the arch's native input size")
     ap.add_argument("--steps", type=int, default=4)
     args = ap.parse_args()
+    args.size = args.size or (128 if args.arch == "tiny" else 416)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
