@@ -174,7 +174,7 @@ __device__ __forceinline__ void chunk_generic(const GemmKArgs& p, float (&v)[32]
 template <int EPI>
 __device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], const ChunkCtx& cx, int lane,
                                            float* st0, float* st1, const CUtensorMap* tmD, uint8_t* stg, int trow,
-                                           int b_in, int b_out, unsigned flags) {
+                                           int b_in, int b_out, unsigned flags, const uint4 (&rq)[4], bool rq_ok) {
   if (flags & F_BIAS) {
     const float4* bp = reinterpret_cast<const float4*>(p.bias + cx.ncol0);
 #pragma unroll
@@ -188,11 +188,12 @@ __device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], c
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if constexpr (EPI == EPI_RESID) {
-    if (cx.row_in) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + cx.rrow + cx.dcol);
+    // the residual chunk was fetched one chunk ahead (see the epilogue loop): its DRAM latency overlaps the
+    // previous chunk's TMEM read / convert / store instead of stalling this one
+    if (rq_ok) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 q = rp[j];
+        const uint4 q = rq[j];
         const float2 e0 = unpack_bf16x2(q.x), e1 = unpack_bf16x2(q.y), e2 = unpack_bf16x2(q.z), e3 = unpack_bf16x2(q.w);
         v[8 * j] += e0.x; v[8 * j + 1] += e0.y; v[8 * j + 2] += e1.x; v[8 * j + 3] += e1.y;
         v[8 * j + 4] += e2.x; v[8 * j + 5] += e2.y; v[8 * j + 6] += e3.x; v[8 * j + 7] += e3.y;
@@ -269,7 +270,25 @@ __device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], c
       }
     }
   }
-  if constexpr (EPI == EPI_STATS) chunk_colstats(p, v, cx.ncol0, lane, st0, st1);
+  if constexpr (EPI == EPI_STATS) {
+    if ((flags & F_TMA) && !(flags & F_DFP32)) {
+      // column statistics straight from the bf16 staging box (the rounded values that are stored): lane L sums
+      // column L over the 32 rows with conflict-free 2-byte shared loads instead of a 62-shuffle butterfly
+      const int jc = lane >> 3, e = (lane & 7) * 2;
+      float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; r += 2) {
+        const float x0 = bf2f(*reinterpret_cast<const __nv_bfloat16*>(stg + r * 64 + ((jc ^ ((r >> 1) & 3)) << 4) + e));
+        const float x1 = bf2f(*reinterpret_cast<const __nv_bfloat16*>(stg + (r + 1) * 64 + ((jc ^ ((r >> 1) & 3)) << 4) + e));
+        sa += x0; qa = fmaf(x0, x0, qa);
+        sb += x1; qb = fmaf(x1, x1, qb);
+      }
+      st0[lane] = sa + sb;
+      st1[lane] = qa + qb;
+    } else {
+      chunk_colstats(p, v, cx.ncol0, lane, st0, st1);
+    }
+  }
 }
 
 struct TileCoord {
@@ -322,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  __shared__ float s_stats[4][2][BN];
+  __shared__ float s_stats[2][4][2][BN];  // double-buffered per tile: one named barrier per tile suffices
   __shared__ __align__(1024) uint8_t s_stage[EPI_WARPS][2048];  // per-warp 32 x 64 B box for TMA tile stores
 
   const int warp = threadIdx.x >> 5;
@@ -441,7 +460,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     float alpha = p.alpha;
     int ncols = p.N;
     asm volatile("" : "+r"(flags), "+f"(alpha), "+r"(ncols));  // pin in ordinary registers (see F_* above)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int tcount = 0;
+    // residual operand of the NEXT chunk this warp will process (EPI_RESID fast path), fetched one chunk ahead
+    uint4 rnext[4] = {};
+    bool rnext_ok = false;
+    auto fetch_resid = [&](const TileCoord& q, int c2) {
+      rnext_ok = false;
+      if constexpr (EPI == EPI_RESID) {
+        const long long row2 = (long long)q.m0 + wq * 32 + lane;
+        if ((flags & F_FAST) && row2 < p.M && q.n0 + c2 * 32 + 32 <= ncols) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)q.b_out * p.strideR +
+              (long long)q.b_in * p.strideR2 + row2 * p.ldr + q.n0 + c2 * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = rp[j];
+          rnext_ok = true;
+        }
+      }
+    };
+    if constexpr (EPI == EPI_RESID) {
+      if ((int)blockIdx.x < total_tiles && chalf < NCHUNK)
+        fetch_resid(decode_tile(p, blockIdx.x, tiles_n, tiles_m, BN), chalf);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
       const int n0 = tc.n0, ztap = tc.ztap;
       const long long row = (long long)tc.m0 + wq * 32 + lane;
@@ -464,6 +505,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       CRIS_TRACE(acc, 0);
 #pragma unroll 1
       for (int c = chalf; c < NCHUNK; c += 2) {
+        uint4 rcur[4] = {};
+        bool rcur_ok = false;
+        if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+          rcur_ok = rnext_ok;
+          if (c + 2 < NCHUNK) {
+            fetch_resid(tc, c + 2);
+          } else if (tile + (int)gridDim.x < total_tiles) {
+            fetch_resid(decode_tile(p, tile + gridDim.x, tiles_n, tiles_m, BN), chalf);
+          } else {
+            rnext_ok = false;
+          }
+        }
         float v[32];
         if (has_acc) {
           uint32_t r[32];
@@ -490,14 +545,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         cx.ncol0 = n0 + c * 32;
         cx.dcol = dcol0 + c * 32;
         cx.drow = drow; cx.rrow = rrow; cx.ztap = ztap; cx.row_in = row_in; cx.row_valid = row_valid;
-        float* st0 = &s_stats[wq][0][c * 32];
-        float* st1 = &s_stats[wq][1][c * 32];
+        float* st0 = &s_stats[tcount & 1][wq][0][c * 32];
+        float* st1 = &s_stats[tcount & 1][wq][1][c * 32];
         if (cx.ncol0 >= ncols) {
           if (flags & F_STATS) { st0[lane] = 0.f; st1[lane] = 0.f; }
           continue;
         }
         if ((flags & F_FAST) && (cx.ncol0 + 32 <= ncols || ((flags & F_TMA) && EPI == EPI_PLAIN && !(flags & F_BIAS))))
-          chunk_fast<EPI>(p, v, cx, lane, st0, st1, &tmD, s_stage[warp], tc.m0 + wq * 32, tc.b_in, tc.b_out, flags);
+          chunk_fast<EPI>(p, v, cx, lane, st0, st1, &tmD, s_stage[warp], tc.m0 + wq * 32, tc.b_in, tc.b_out, flags, rcur,
+                          rcur_ok);
         else chunk_generic(p, v, cx, lane, st0, st1);
       }
       CRIS_TRACE(acc, 14);
@@ -505,15 +561,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int j = threadIdx.x; j < BN; j += EPI_WARPS * 32) {
           if (n0 + j < p.N) {
-            const float s0 = s_stats[0][0][j] + s_stats[1][0][j] + s_stats[2][0][j] + s_stats[3][0][j];
-            const float s1 = s_stats[0][1][j] + s_stats[1][1][j] + s_stats[2][1][j] + s_stats[3][1][j];
+            const float(*ss)[2][BN] = s_stats[tcount & 1];
+            const float s0 = ss[0][0][j] + ss[1][0][j] + ss[2][0][j] + ss[3][0][j];
+            const float s1 = ss[0][1][j] + ss[1][1][j] + ss[2][1][j] + ss[3][1][j];
             // 64 partial rows (m_tile % 64): spreads the atomics, keeps the follow-up reduction tiny
             float* dst = p.colstats + (size_t)((tc.m0 / BM) & 63) * 2 * p.N;
             atomicAdd(dst + n0 + j, s0);
             atomicAdd(dst + p.N + n0 + j, s1);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // s_stats is reused by the next tile
+        // no second barrier: the next tile fills the other s_stats buffer, and this buffer is only rewritten two
+        // tiles later, i.e. after every warp passed the next tile's barrier (hence finished these reads)
       }
       if (has_acc) ++acc;
     }

@@ -77,6 +77,34 @@ def test_eval_forward_matches_fp32_oracle(tiny):
     assert float(flips.float().mean()) < 0.02
 
 
+def test_eval_graph_equals_eager_and_tracks_weights(tiny):
+    """The captured inference graph gives the eager launches' result bit for bit, returns fresh tensors, and
+    re-reads parameters / running statistics at replay time (an in-place weight update changes the output)."""
+    cfg, sd, model = tiny
+    eng = model._get_engine()
+    img, word, _ = synth.make_inputs(2, 3, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    img, word = img.cuda(), word.cuda()
+    model.eval()
+    with torch.no_grad():
+        eng.use_graphs = False
+        eager = model(img, word).clone()
+        eng.use_graphs = True
+        g1 = model(img, word)
+        g2 = model(img, word)
+        assert eng.eval_graphs, "the inference graph was not used"
+        assert torch.equal(g1, eager) and torch.equal(g2, eager) and g1.data_ptr() != g2.data_ptr()
+        w = model.proj.txt.weight
+        w.mul_(1.5)
+        try:
+            changed = model(img, word)
+            eng.use_graphs = False
+            eager2 = model(img, word)
+            eng.use_graphs = True
+        finally:
+            w.div_(1.5)
+        assert not torch.equal(changed, eager) and torch.equal(changed, eager2)
+
+
 def test_eval_matches_reference_golden(tiny, golden_dir):
     cfg, sd, model = tiny
     g = torch.load(os.path.join(golden_dir, "tiny_b2_128.pt"), weights_only=False)
