@@ -184,7 +184,11 @@ def main():
     if world > 1:  # train.py:97-102
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-    opt = torch.optim.Adam(groups, lr=1e-4, weight_decay=0.0)  # train.py:105-107
+    if os.environ.get("CRIS_B200_TORCH_ADAM", "0") == "1":
+        opt = torch.optim.Adam(groups, lr=1e-4, weight_decay=0.0)  # train.py:105-107, stock optimizer
+    else:  # same update, one launch per parameter group (cris/pytorch_b200/optim.py)
+        from cris.pytorch_b200.optim import Adam
+        opt = Adam(groups, lr=1e-4, weight_decay=0.0)
     scaler = torch.amp.GradScaler("cuda")                          # train.py:111
     vocab = synth.ARCHS[args.arch]["vocab"]
     img_h, word_h, mask_h = synth.make_inputs(B, rank, size, cfg.word_len, vocab)

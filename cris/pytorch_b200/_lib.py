@@ -78,6 +78,7 @@ _SIGS = {
     "cris_small_matmul": "pppiiiiip",
     "cris_dynconv_bce_fwd": "pqpqpiipppiiiip",
     "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
+    "cris_adam_step": "piqddddddppp",
 }
 
 _lib = None
@@ -120,7 +121,7 @@ def exported_symbols():
     return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
             "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_args_size", "cris_gemm_args_last_offset",
             "cris_peer_buffer_bytes", "cris_peer_buffer_create", "cris_peer_buffer_open", "cris_peer_buffer_close",
-            "cris_peer_allreduce_f32", *_SIGS.keys()]
+            "cris_peer_allreduce_f32", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

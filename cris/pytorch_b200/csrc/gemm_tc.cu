@@ -657,6 +657,32 @@ static int pick_bn(const cris_gemm_args* a, int max_bn) {
   return a->N <= 32 ? 32 : 64;
 }
 
+// split-K plan of an fp32-accumulating GEMM (wgrad): tile width and split count are chosen together so that the work
+// units fill whole waves of the persistent grid (two waves: the epilogue atomics of one unit overlap the next
+// unit's main loop).  The widest tile that keeps >= 90% of its waves busy wins (wide tiles re-read A less).
+static void plan_split_k(const cris_gemm_args* a, int* bn_out, int* splits_out) {
+  const long long z = (long long)a->batch * (a->tap_mode == CRIS_TAP_WGRAD ? a->taps : 1);
+  const long long tm = (a->M + BM - 1) / BM;
+  const int nkb = (a->K + 63) / 64;
+  const int sms = num_sms();
+  double best = -1.0;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (bn > 64 && a->N <= bn / 2) continue;
+    const long long tiles = tm * ((a->N + bn - 1) / bn) * z;
+    long long s = tiles >= 2 * sms ? 1 : (2 * sms) / tiles;
+    if (s > nkb / 4) s = nkb / 4;
+    if (s < 1) s = 1;
+    const long long units = tiles * s, waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    if (eff > best) {
+      best = eff;
+      *bn_out = bn;
+      *splits_out = (int)s;
+    }
+    if (eff >= 0.9) break;
+  }
+}
+
 template <int BN, int BK, bool A_MN, bool B_MN, int EPI>
 static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
   using Cfg = TileCfg<BN, BK>;
@@ -747,12 +773,18 @@ int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream);  // gemm_ref.
 static std::atomic<int> g_gemm_impl{0};
 static long long* g_trace = nullptr;  // debug timeline buffer (cris_debug_set_trace)
 
-int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
-  CRIS_CHECK_ARG(a != nullptr, "null gemm args");
+int gemm_dispatch(const cris_gemm_args* a_in, cudaStream_t stream) {
+  CRIS_CHECK_ARG(a_in != nullptr, "null gemm args");
+  cris_gemm_args planned = *a_in;
+  int planned_bn = 0;
+  if (planned.splits == 0 && planned.accumulate && planned.d_fp32 && planned.M > 0 && planned.N > 0 && planned.K > 0 &&
+      planned.batch >= 1)
+    plan_split_k(&planned, &planned_bn, &planned.splits);
+  const cris_gemm_args* a = &planned;
   CRIS_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch >= 1, "bad GEMM shape M=%d N=%d K=%d batch=%d", a->M,
                  a->N, a->K, a->batch);
   CRIS_CHECK_ARG(a->tap_mode == CRIS_TAP_NONE || (a->taps >= 1 && a->taps <= 9), "bad tap count %d", a->taps);
-  CRIS_CHECK_ARG(a->splits >= 1, "splits must be >= 1");
+  CRIS_CHECK_ARG(a->splits >= 1, "splits must be >= 1 (0 = automatic, fp32-accumulating GEMMs only)");
   CRIS_CHECK_ARG(a->splits == 1 || (a->d_fp32 && a->accumulate), "split-K needs fp32 atomic accumulation");
   CRIS_CHECK_ARG(!a->accumulate || a->d_fp32, "accumulate needs fp32 D");
   CRIS_CHECK_ARG(a->d_col_stride <= 1 || a->accumulate, "d_col_stride needs accumulate mode");
@@ -786,7 +818,7 @@ int gemm_dispatch(const cris_gemm_args* a, cudaStream_t stream) {
     if (a->N <= 64) return launch_tc<64, 32, false, false>(a, k, stream);
     return launch_tc<128, 32, false, false>(a, k, stream);
   }
-  const int bn = pick_bn(a, 256);
+  const int bn = planned_bn ? planned_bn : pick_bn(a, 256);
   if (!amn && !bmn) {
     if (bn == 32) return launch_tc<32, 64, false, false>(a, k, stream);
     if (bn == 64) return launch_tc<64, 64, false, false>(a, k, stream);

@@ -556,12 +556,6 @@ class Run:
         wp = geom[2] + 2
         return [dy * wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
 
-    @staticmethod
-    def wgrad_splits(m_tiles, n_tiles, taps, K):
-        tiles = m_tiles * n_tiles * taps
-        nkb = (K + 63) // 64
-        return max(1, min(nkb, (2 * 148 + tiles - 1) // tiles))
-
     def col_sum(self, m: Mat, width: int, hp=0, wp=0) -> torch.Tensor:
         """per-column sums of m[:, :width] (bias gradients); fp32 vector of the padded width."""
         wpad = _r8(width)
@@ -697,7 +691,7 @@ class Run:
             # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
             gw = self.pg(wname)
             gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
-            splits = self.wgrad_splits((cout + 127) // 128, (cin + 127) // 128, 9 if k == 3 else 1, x.rows)
+            splits = 0  # the library plans tile width and split-K together (whole waves of its persistent grid)
             if k == 3:
                 self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
                           d_tap_n=1, d_col_stride=9, splits=splits, accumulate=1)
@@ -797,11 +791,11 @@ class Run:
             gw = self.pg(wname)
             if transposed_weight:
                 gwm = Mat(gw, n_in, n_out, fp32=True)
-                sp = self.wgrad_splits((n_in + 127) // 128, (n_out + 127) // 128, 1, x.rows)
+                sp = 0
                 self.gemm(x, dy, gwm, n_in, n_out, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
             else:
                 gwm = Mat(gw, n_out, n_in, fp32=True, ptr=gw.data_ptr() + 4 * r0 * n_in)
-                sp = self.wgrad_splits((n_out + 127) // 128, (n_in + 127) // 128, 1, x.rows)
+                sp = 0
                 self.gemm(dy, x, gwm, n_out, n_in, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
             if x.need_grad:
                 slot, acc = self.grad_slot(x)

@@ -1,0 +1,125 @@
+"""Adam with the whole parameter-group update in one kernel launch (csrc/optim.cu; SURVEY §8f "next" row).
+
+Drop-in for the optimizer the reference builds at train.py:105-107 (`torch.optim.Adam(param_list, lr, weight_decay)`)
+and drives through `GradScaler` (engine/engine.py:52-57): same constructor arguments, same `state_dict()` layout
+(`step`, `exp_avg`, `exp_avg_sq` per parameter, so checkpoints move between the two), same update arithmetic
+(L2 weight decay folded into the gradient, bias-corrected moments), `MultiStepLR` works on `param_groups[i]["lr"]`.
+`_step_supports_amp_scaling` makes `scaler.step(optimizer)` hand over the loss scale and the found-inf flag: the
+kernel un-scales gradients on the fly, and a step with non-finite gradients is skipped entirely.
+No CPU fallback: parameters must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Adam(torch.optim.Optimizer):
+    _step_supports_amp_scaling = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, *,
+                 maximize=False, decoupled_weight_decay=False):
+        if amsgrad or maximize or decoupled_weight_decay:
+            raise NotImplementedError("cris.pytorch_b200.optim.Adam: amsgrad / maximize / decoupled weight decay are "
+                                      "not implemented (the reference uses none of them, train.py:105-107)")
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")
+        # the extra keys keep state_dict()s interchangeable with torch.optim.Adam
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None,
+                        decoupled_weight_decay=False)
+        super().__init__(params, defaults)
+        self._tables: Dict[int, Tuple[tuple, torch.Tensor, int, int]] = {}
+        # GradScaler's found-inf flag of the previous step() and the parameters whose counters it advanced: the flag
+        # is read on the host one step late, so step() never waits for the GPU (see _resolve_pending)
+        self._pending: Tuple[torch.Tensor, list] | None = None
+
+    def _table(self, gi: int, params: List[torch.Tensor], grads, ms, vs):
+        """Device table of one group, rebuilt only when a pointer changed (the caching allocator usually hands the
+        freshly allocated .grad tensors the same blocks every step)."""
+        key = tuple(t.data_ptr() for ts in (params, grads, ms, vs) for t in ts)
+        ent = self._tables.get(gi)
+        if ent is not None and ent[0] == key:
+            return ent[1], ent[2], ent[3]
+        L = _lib.lib()
+        chunk = L.cris_adam_chunk_elems()
+        n = len(params)
+        tab = np.zeros((n, 6), dtype=np.int64)
+        assert L.cris_adam_table_entry_bytes() == tab.strides[0]
+        tab[:, 0] = [p.data_ptr() for p in params]
+        tab[:, 1] = [g.data_ptr() for g in grads]
+        tab[:, 2] = [m.data_ptr() for m in ms]
+        tab[:, 3] = [v.data_ptr() for v in vs]
+        tab[:, 4] = [p.numel() for p in params]
+        chunks = (tab[:, 4] + chunk - 1) // chunk
+        tab[:, 5] = np.cumsum(chunks) - chunks
+        dev = torch.from_numpy(tab).to(params[0].device)
+        total = int(chunks.sum())
+        self._tables[gi] = (key, dev, n, total)
+        return dev, n, total
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        grad_scale = getattr(self, "grad_scale", None)
+        found_inf = getattr(self, "found_inf", None)
+        # GradScaler semantics: a step that saw inf/nan gradients changes nothing, not even the step counters.  The
+        # kernel tests the device flag itself; the host-side counters are advanced optimistically and rolled back
+        # when the flag is read at the next call (by then the GPU is long past it), so no step waits on the device.
+        self._resolve_pending()
+        advanced = []
+        L = _lib.lib()
+        for gi, group in enumerate(self.param_groups):
+            by_step: Dict[float, list] = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
+                    raise RuntimeError("cris.pytorch_b200.optim.Adam needs dense fp32 CUDA parameters and gradients "
+                                       "(no CPU fallback)")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                advanced.append(st)
+                by_step.setdefault(float(st["step"]), []).append(p)
+            for si, (step, params) in enumerate(sorted(by_step.items())):
+                params = [p for p in params]
+                grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in params]
+                if any(not p.is_contiguous() for p in params):
+                    raise RuntimeError("cris.pytorch_b200.optim.Adam needs contiguous parameters")
+                ms = [self.state[p]["exp_avg"] for p in params]
+                vs = [self.state[p]["exp_avg_sq"] for p in params]
+                tab, n, total = self._table(gi * 1024 + si, params, grads, ms, vs)
+                with torch.cuda.device(params[0].device):
+                    rc = L.cris_adam_step(tab.data_ptr(), n, total, float(group["lr"]), float(group["betas"][0]),
+                                          float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
+                                          float(step), grad_scale.data_ptr() if grad_scale is not None else None,
+                                          found_inf.data_ptr() if found_inf is not None else None, _lib.stream_ptr())
+                if rc != 0:
+                    raise RuntimeError(f"libcris_b200 cris_adam_step failed: {L.cris_last_error().decode()}")
+        if found_inf is not None:
+            self._pending = (found_inf, advanced)
+        return loss
+
+    def _resolve_pending(self):
+        if self._pending is not None:
+            flag, advanced = self._pending
+            self._pending = None
+            if float(flag.item()) != 0.0:
+                for st in advanced:
+                    st["step"] -= 1
+
+    def state_dict(self):
+        self._resolve_pending()
+        return super().state_dict()

@@ -63,6 +63,8 @@ enum { CRIS_TAP_NONE = 0, CRIS_TAP_ACCUM = 1, CRIS_TAP_WGRAD = 2 };
  *   Out-of-range rows/columns read as zero (TMA zero fill).
  * splits > 1 divides the K loop over `splits` CTAs that atomically add into fp32 D
  * (requires d_fp32 = 1, accumulate = 1; D pre-zeroed by the caller unless accumulating).
+ * splits = 0 with accumulate = 1 lets the library choose tile width and split count together so that the work
+ * units fill whole waves of its persistent grid.
  * Epilogue order: acc*alpha -> +bias[n] -> act -> +resid -> row mask -> store / atomic add
  *   -> optional per-column (sum, sumsq) partials of the stored values atomically added into
  *      colstats[(m/128) % 64][2][N] (fp32, zeroed by the caller) — the BatchNorm batch statistics.
@@ -232,6 +234,19 @@ int cris_peer_buffer_close(void* dev_ptr, int owned);
  * timeout_s <= 0 -> 120 s; a peer that never arrives makes the kernel print and trap instead of hanging. */
 int cris_peer_allreduce_f32(void* const* peer_ptrs, int world, int rank, int slot, const float* in, float* out, int n,
                             double timeout_s, void* stream);
+
+/* ---- optimizer step (SURVEY 8f "next" row: torch.optim.Adam driven by GradScaler, train.py:105-111,
+ *      engine/engine.py:52-57).  One launch updates every tensor of a parameter group:
+ *      g' = g / *grad_scale (+ weight_decay * p); m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
+ *      table_dev: DEVICE array of n_tensors entries {float* p; const float* g; float* m; float* v; int64 n;
+ *      int64 chunk0} where chunk0 is the exclusive prefix sum of ceil(n / cris_adam_chunk_elems()) and n_chunks the
+ *      total.  `step` is the step count after this update (bias correction).  *found_inf != 0 skips the update
+ *      (GradScaler semantics); either pointer may be NULL. */
+int cris_adam_table_entry_bytes(void);
+int cris_adam_chunk_elems(void);
+int cris_adam_step(const void* table_dev, int n_tensors, long long n_chunks, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, double step, const float* grad_scale, const float* found_inf,
+                   void* stream);
 
 #ifdef __cplusplus
 }

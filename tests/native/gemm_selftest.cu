@@ -96,6 +96,8 @@ static std::vector<Case> make_cases() {
   // conv wgrad: one slab per tap, split-K, fp32 atomics
   { auto x = add("conv_wgrad_c128_c64", 128, 64, 3 * 10 * 12, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 10; x->wp = 12; x->d_fp32 = 1; x->accumulate = 1; x->splits = 2; x->cpu_check = 1; }
   { auto x = add("conv_wgrad_c256_c256", 256, 256, 6 * 28 * 28, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 28; x->wp = 28; x->d_fp32 = 1; x->accumulate = 1; x->splits = 4; }
+  { auto x = add("conv_wgrad_auto_split", 256, 512, 8 * 26 * 26, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 26; x->wp = 26; x->d_fp32 = 1; x->accumulate = 1; x->splits = 0; }
+  { auto x = add("tn_wgrad_lin_auto_split", 512, 640, 9000, 1, 1, 1); x->d_fp32 = 1; x->accumulate = 1; x->splits = 0; }
   { auto x = add("conv_wgrad_c32_c32", 32, 32, 2 * 30 * 30, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 30; x->wp = 30; x->d_fp32 = 1; x->accumulate = 1; x->splits = 3; }
   return c;
 }
@@ -368,6 +370,7 @@ static void perf(int only = -1) {
       {"conv1x1 64x(106x106) 256->64", 64 * 106 * 106, 64, 256, 1, 106, 106, 0, 0},
       {"dgrad 43264x512x2048 (B MN)", 43264, 512, 2048, 1, 0, 0, 0, 1},
       {"wgrad 512x512x43264 (A,B MN)", 512, 512, 43264, 1, 0, 0, 1, 1},
+      {"wgrad 256x512x719104 (A,B MN)", 256, 512, 719104, 1, 0, 0, 1, 1},
   };
   int pi = -1;
   for (const P& q : ps) {
@@ -386,7 +389,7 @@ static void perf(int only = -1) {
     CK(cudaMalloc(&A, a_rows * a_cols * 2)); CK(cudaMalloc(&B, b_rows * b_cols * 2)); CK(cudaMalloc(&D, (size_t)q.M * q.N * (wg ? 4 : 2)));
     CK(cudaMemset(A, 0x3c, a_rows * a_cols * 2)); CK(cudaMemset(B, 0x3c, b_rows * b_cols * 2)); CK(cudaMemset(D, 0, (size_t)q.M * q.N * (wg ? 4 : 2)));
     a.A = A; a.B = B; a.D = D;
-    if (wg) { a.d_fp32 = 1; a.accumulate = 1; a.splits = 16; }
+    if (wg) { a.d_fp32 = 1; a.accumulate = 1; a.splits = 0; }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i) if (cris_gemm(&a, nullptr)) { printf("launch error %s\n", cris_last_error()); return; }
     CK(cudaDeviceSynchronize());

@@ -21,7 +21,8 @@ def main():
     dev = torch.device("cuda", 0)
     cfg, model, groups = bench.build_model(arch, dropout=0.1)
     model = model.to(dev).train()
-    opt = torch.optim.Adam(groups, lr=1e-4)
+    from cris.pytorch_b200.optim import Adam
+    opt = Adam(groups, lr=1e-4)
     scaler = torch.amp.GradScaler("cuda")
     size = 416 if arch != "tiny" else 128
     img, word, mask = synth.make_inputs(B, 0, size, cfg.word_len, synth.ARCHS[arch]["vocab"])

@@ -16,7 +16,8 @@ def main():
     dev = torch.device("cuda", 0)
     cfg, model, groups = bench.build_model("r50", dropout=0.1)
     model = model.to(dev).train()
-    opt = torch.optim.Adam(groups, lr=1e-4)
+    from cris.pytorch_b200.optim import Adam
+    opt = (torch.optim.Adam if os.environ.get("CRIS_B200_TORCH_ADAM") == "1" else Adam)(groups, lr=1e-4)
     scaler = torch.amp.GradScaler("cuda")
     img, word, mask = synth.make_inputs(B, 0, 416, cfg.word_len, synth.ARCHS["r50"]["vocab"])
     img, word, mask = img.to(dev), word.to(dev), mask.to(dev)
