@@ -79,4 +79,30 @@ __device__ __forceinline__ bool interior_row(long long r, int hp, int wp) {
   return (h >= 1u) && (h <= (unsigned)(hp - 2)) && (w >= 1u) && (w <= (unsigned)(wp - 2));
 }
 
+// (h, w) of a padded-NHWC row index, advanced incrementally: kernels that walk rows with a constant stride test
+// "interior pixel?" without the two integer divisions interior_row() costs per call
+struct RowWalker {
+  int h, w, hp, wp;
+  __device__ __forceinline__ void init(long long row, int hp_, int wp_) {
+    hp = hp_; wp = wp_; h = 0; w = 0;
+    if (wp > 0) {
+      const unsigned rr = (unsigned)row % (unsigned)(hp * wp);
+      h = (int)(rr / (unsigned)wp);
+      w = (int)(rr - (unsigned)h * (unsigned)wp);
+    }
+  }
+  __device__ __forceinline__ bool interior() const {
+    return wp <= 0 || (h >= 1 && h <= hp - 2 && w >= 1 && w <= wp - 2);
+  }
+  __device__ __forceinline__ void advance(int step) {
+    if (wp > 0) {
+      w += step;
+      while (w >= wp) {
+        w -= wp;
+        if (++h == hp) h = 0;
+      }
+    }
+  }
+};
+
 }  // namespace cris

@@ -41,10 +41,9 @@ __global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs 
 #pragma unroll
     for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
     const int c = g * 8;
-    float mu[8], rs[8], sc[8], sh[8];
+    float mu[8], sc[8], sh[8];
     if (MODE == 1) {
       ld8f(p.mean + c, mu);
-      ld8f(p.rstd + c, rs);
       if (p.relu && p.y == nullptr) {
         ld8f(p.scale + c, sc);
         ld8f(p.shift + c, sh);
@@ -53,13 +52,16 @@ __global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs 
     if (tr < R) {
       // U rows per trip: all loads of a trip are issued before any is consumed (memory-level parallelism)
       constexpr int U = (MODE == 1) ? 2 : 4;
+      RowWalker rw;
+      rw.init(r0 + tr, MODE == 3 ? 0 : p.hp, MODE == 3 ? 0 : p.wp);
       for (long long rb = r0 + tr; rb < r1; rb += (long long)R * U) {
         float a[U][8], xv[U][8], yv[U][8];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long r = rb + (long long)u * R;
-          ok[u] = r < r1 && (MODE == 3 || interior_row(r, p.hp, p.wp));
+          ok[u] = r < r1 && rw.interior();
+          rw.advance(R);
           if (ok[u]) {
             ld8x(p.a, r * p.lda + c, p.a_fp32, a[u]);
             if (MODE == 1 || MODE == 3) ld8x(p.x, r * p.ldx + c, p.x_fp32, xv[u]);
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs 
               }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] += a[u][i] * (xv[u][i] - mu[i]) * rs[i]; }
+            for (int i = 0; i < 8; ++i) { s0[i] += a[u][i]; s1[i] = fmaf(a[u][i], xv[u][i] - mu[i], s1[i]); }
           } else {
             if (p.a2 != nullptr) {
 #pragma unroll
@@ -100,6 +102,12 @@ __global__ void __launch_bounds__(256, 2) col_reduce_kernel(const ColReduceArgs 
           }
         }
       }
+    }
+    if (MODE == 1) {  // the per-channel 1/std factor of xhat is applied once, not per element
+      float rs[8];
+      ld8f(p.rstd + c, rs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s1[i] *= rs[i];
     }
     // reduce over the R row-lanes that share this channel group
     __syncthreads();

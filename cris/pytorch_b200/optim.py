@@ -34,23 +34,36 @@ class Adam(torch.optim.Optimizer):
                         foreach=None, capturable=False, differentiable=False, fused=None,
                         decoupled_weight_decay=False)
         super().__init__(params, defaults)
-        self._tables: Dict[int, Tuple[tuple, torch.Tensor, int, int]] = {}
+        self._tables: Dict[int, dict] = {}
+        self.table_refreshes = 0
         # GradScaler's found-inf flag of the previous step() and the parameters whose counters it advanced: the flag
         # is read on the host one step late, so step() never waits for the GPU (see _resolve_pending)
-        self._pending: Tuple[torch.Tensor, list] | None = None
+        self._pending = None
+        self._flag_host = None
+        self._flag_turn = 0
 
     def _table(self, gi: int, params: List[torch.Tensor], grads, ms, vs):
-        """Device table of one group, rebuilt only when a pointer changed (the caching allocator usually hands the
-        freshly allocated .grad tensors the same blocks every step)."""
+        """Device table of one group, refreshed only when a pointer changed (the caching allocator usually hands the
+        freshly allocated .grad tensors the same blocks every step).  The refresh is an asynchronous copy from a
+        small ring of pinned staging buffers, so it never makes the host wait for the backward pass in flight."""
         key = tuple(t.data_ptr() for ts in (params, grads, ms, vs) for t in ts)
         ent = self._tables.get(gi)
-        if ent is not None and ent[0] == key:
-            return ent[1], ent[2], ent[3]
+        if ent is not None and ent["key"] == key:
+            return ent["dev"], ent["n"], ent["total"]
         L = _lib.lib()
         chunk = L.cris_adam_chunk_elems()
         n = len(params)
-        tab = np.zeros((n, 6), dtype=np.int64)
-        assert L.cris_adam_table_entry_bytes() == tab.strides[0]
+        if ent is None or ent["n"] != n:
+            ent = {"dev": torch.empty((n, 6), dtype=torch.int64, device=params[0].device),
+                   "pinned": [torch.empty((n, 6), dtype=torch.int64).pin_memory() for _ in range(4)],
+                   "events": [None] * 4, "turn": 0, "n": n}
+            assert L.cris_adam_table_entry_bytes() == 6 * 8
+            self._tables[gi] = ent
+        slot = ent["turn"] % 4
+        ent["turn"] += 1
+        if ent["events"][slot] is not None:
+            ent["events"][slot].synchronize()  # that staging buffer's previous upload (4 refreshes ago) is done
+        tab = ent["pinned"][slot].numpy()
         tab[:, 0] = [p.data_ptr() for p in params]
         tab[:, 1] = [g.data_ptr() for g in grads]
         tab[:, 2] = [m.data_ptr() for m in ms]
@@ -58,10 +71,14 @@ class Adam(torch.optim.Optimizer):
         tab[:, 4] = [p.numel() for p in params]
         chunks = (tab[:, 4] + chunk - 1) // chunk
         tab[:, 5] = np.cumsum(chunks) - chunks
-        dev = torch.from_numpy(tab).to(params[0].device)
-        total = int(chunks.sum())
-        self._tables[gi] = (key, dev, n, total)
-        return dev, n, total
+        with torch.cuda.device(params[0].device):
+            ent["dev"].copy_(ent["pinned"][slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ent["events"][slot] = ev
+        ent["key"], ent["total"] = key, int(chunks.sum())
+        self.table_refreshes += 1
+        return ent["dev"], n, ent["total"]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -109,14 +126,25 @@ class Adam(torch.optim.Optimizer):
                 if rc != 0:
                     raise RuntimeError(f"libcris_b200 cris_adam_step failed: {L.cris_last_error().decode()}")
         if found_inf is not None:
-            self._pending = (found_inf, advanced)
+            # the flag travels to pinned host memory behind this step's kernels; reading it next time waits on that
+            # copy's event only (a plain .item() would drain the whole stream, i.e. the next backward pass)
+            if self._flag_host is None:
+                self._flag_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            host = self._flag_host[self._flag_turn & 1]
+            self._flag_turn += 1
+            with torch.cuda.device(found_inf.device):
+                host.copy_(found_inf.reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            self._pending = (host, ev, advanced)
         return loss
 
     def _resolve_pending(self):
         if self._pending is not None:
-            flag, advanced = self._pending
+            host, ev, advanced = self._pending
             self._pending = None
-            if float(flag.item()) != 0.0:
+            ev.synchronize()
+            if float(host[0]) != 0.0:
                 for st in advanced:
                     st["step"] -= 1
 

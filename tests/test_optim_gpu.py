@@ -70,7 +70,8 @@ def test_adam_under_gradscaler_skips_inf_steps_and_interoperates_with_torch_stat
     for c, b in zip(pc, pb):
         c.data.copy_(b.data)
     oc = Adam(_groups(pc), lr=2e-3)
-    oc.load_state_dict(ob.state_dict())
+    import copy
+    oc.load_state_dict(copy.deepcopy(ob.state_dict()))  # (load_state_dict keeps references to same-device tensors)
     _set_grads(pc, pb, 9)
     oc.step(); ob.step()
     for c, b in zip(pc, pb):

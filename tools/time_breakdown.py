@@ -44,6 +44,7 @@ def main():
         if it >= 3:
             print(f"it {it}: gpu fwd {ev[0].elapsed_time(ev[1]):7.2f} bwd {ev[1].elapsed_time(ev[2]):7.2f} opt {ev[2].elapsed_time(ev[3]):7.2f} "
                   f"metric {ev[3].elapsed_time(ev[4]):6.2f} | host fwd {1e3*(t1-t0):6.2f} bwd {1e3*(t2-t1):6.2f} opt {1e3*(t3-t2):6.2f} rest {1e3*(t4-t3):6.2f} | total {1e3*(t4-t0):7.2f} ms loss {l:.4f}")
+    print("adam table refreshes", getattr(opt, "table_refreshes", None))
     print("mem GB", torch.cuda.max_memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9)
 
 
