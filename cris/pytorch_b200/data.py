@@ -17,13 +17,25 @@ from typing import Iterable, Iterator
 import torch
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """One staging stream per device for the life of the process: the caching allocator keeps freed blocks per
+    stream, so a new stream per epoch would re-allocate the staging buffers (a ~100 ms cudaMalloc stall each)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class DevicePrefetcher:
     def __init__(self, loader: Iterable, device=None):
         self.loader = loader
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher stages batches onto a CUDA device (no CPU fallback)")
-        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream = _side_stream(self.device)
 
     def __len__(self):
         return len(self.loader)
