@@ -123,7 +123,7 @@ def cpu_reference_steps(arch, batch, steps, warmup, threads, size=416):
         for k, v in out["new_running"].items():
             live[k] = v
         train_metric(out["pred"].detach(), out["mask"])
-        float(out["loss"])
+        float(out["loss"].detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times), batch
