@@ -845,6 +845,18 @@ extern "C" {
 int cris_gemm(const cris_gemm_args* args, void* stream) {
   return cris::gemm_dispatch(args, reinterpret_cast<cudaStream_t>(stream));
 }
+int cris_gemm_plan(const cris_gemm_args* args, int* tile_n, int* splits) {
+  CRIS_CHECK_ARG(args != nullptr && tile_n != nullptr && splits != nullptr, "cris_gemm_plan: null argument");
+  CRIS_CHECK_ARG(args->M > 0 && args->N > 0 && args->K > 0 && args->batch >= 1, "cris_gemm_plan: bad shape");
+  if (args->splits == 0 && args->accumulate && args->d_fp32) {
+    cris::plan_split_k(args, tile_n, splits);
+  } else {
+    *tile_n = ((args->K <= 32) && !args->a_mn && !args->b_mn) ? (args->N <= 32 ? 32 : args->N <= 64 ? 64 : 128)
+                                                               : cris::pick_bn(args, 256);
+    *splits = args->splits > 0 ? args->splits : 1;
+  }
+  return 0;
+}
 void cris_set_gemm_impl(int impl) { cris::g_gemm_impl.store(impl); }
 void cris_debug_set_trace(void* dev_buf) { cris::g_trace = reinterpret_cast<long long*>(dev_buf); }
 int cris_get_gemm_impl(void) { return cris::g_gemm_impl.load(); }

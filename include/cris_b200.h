@@ -99,6 +99,9 @@ typedef struct cris_gemm_args {
 } cris_gemm_args;
 
 int cris_gemm(const cris_gemm_args* args, void* stream);
+/* host-only: the tile width (32/64/128/256 output columns per 128-row tile) and split-K count cris_gemm would use
+ * for these arguments on the current device (148 SMs assumed when no device is present) */
+int cris_gemm_plan(const cris_gemm_args* args, int* tile_n, int* splits);
 int cris_gemm_args_size(void);         /* sizeof(cris_gemm_args): lets a binding verify its struct mirror */
 int cris_gemm_args_last_offset(void);  /* offsetof(cris_gemm_args, d_col_stride) */
 
