@@ -223,6 +223,13 @@ class Engine:
                 if gs is None:
                     gs = GraphedStep(self, img, word, mask, names)
                     self.graphs = {key: gs}  # one shape resident at a time (each holds all activations)
+                if len(gs.gbs) > 1:
+                    P = dict(zip(names, params))
+                    K = len(gs.gbs)
+                    pred, mask_r, loss = _GraphFirst.apply(gs, img, word, mask, *[P[n] for n in gs.seg_names[K - 1]])
+                    for k in range(K - 2, -1, -1):
+                        loss = _GraphSeg.apply(gs, k, loss, *[P[n] for n in gs.seg_names[k]])
+                    return pred, mask_r, loss
                 return _GraphFunction.apply(gs, img, word, mask, *params)
             pred, mask_r, loss = _CRISFunction.apply(self, names, img, word, mask, *params)
             return pred, mask_r, loss
@@ -286,9 +293,22 @@ class GraphedStep:
         with torch.cuda.stream(side), torch.no_grad():
             r = Run(engine, self.img, self.word, self.mask, True, record=True)
             r.forward()
+            n_tape = len(r.tape)
             r.backward(self.g, names)
+            touched = dict(r.touched)
             del r
         torch.cuda.current_stream(dev).wait_stream(side)
+        # backward segments (CRIS_B200_BWD_SEGMENTS=K): the reversed tape is cut into K ranges captured as K graphs;
+        # a parameter belongs to the range that writes its gradient last (learnt from the warm-up pass above)
+        K = max(1, min(int(os.environ.get("CRIS_B200_BWD_SEGMENTS", "1")), 8, n_tape))
+        self.bounds = [round(n_tape * k / K) for k in range(K + 1)]
+        self.seg_names: List[List[str]] = [[] for _ in range(K)]
+        for nm in names:
+            pos = touched.get(nm, n_tape - 1)
+            k = next(j for j in range(K) if pos < self.bounds[j + 1] or j == K - 1)
+            self.seg_names[k].append(nm)
+        if any(len(sn) == 0 for sn in self.seg_names):  # every link of the autograd chain needs a parameter
+            self.bounds, self.seg_names = [0, n_tape], [list(names)]
         with torch.no_grad():
             for k, b in engine.model.named_buffers():
                 b.copy_(saved[k])
@@ -304,9 +324,17 @@ class GraphedStep:
                     r.forward()
                 n1 = _lib.launch_count()
                 self.pred, self.mask_out, self.loss = r.pred, r.mask_out, r.loss
-                self.gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.gb, pool=self.gf.pool()):
-                    self.grads = r.backward(self.g, names)
+                self.gbs, self.n_bwds = [], []
+                for k in range(len(self.seg_names)):
+                    gb = torch.cuda.CUDAGraph()
+                    nb0 = _lib.launch_count()
+                    with torch.cuda.graph(gb, pool=self.gf.pool()):
+                        r.backward_range(self.g, self.bounds[k], self.bounds[k + 1] if k + 1 < len(self.seg_names) else None)
+                    self.gbs.append(gb)
+                    self.n_bwds.append(_lib.launch_count() - nb0)
+                self.grads = r.collect_grads(names)
+                self.grad_of_name = dict(zip(names, self.grads))
+                self.gb = self.gbs[0]
                 self.n_fwd, self.n_bwd = n1 - n0, _lib.launch_count() - n1  # kernels inside each graph
                 _lib.lib().cris_add_launch_count(-(self.n_fwd + self.n_bwd) & ((1 << 64) - 1))  # capture != launch
                 self.run = r  # keeps every captured buffer referenced
@@ -389,6 +417,52 @@ class _GraphFunction(torch.autograd.Function):
         return (None, None, None, None, *gs.grads)
 
 
+class _GraphFirst(torch.autograd.Function):
+    """Segmented backward, first link of the chain: replays the forward graph; its backward replays the LAST
+    backward range (the earliest layers) and returns the gradients finalised there."""
+
+    @staticmethod
+    def forward(ctx, gs: GraphedStep, img, word, mask, *params):
+        gs.img.copy_(img)
+        gs.word.copy_(word)
+        gs.mask.copy_(mask)
+        gs.gf.replay()
+        _lib.lib().cris_add_launch_count(gs.n_fwd)
+        ctx.gs = gs
+        pred, mask_out, loss = gs.pred.detach(), gs.mask_out.detach(), gs.loss.detach().clone()
+        ctx.mark_non_differentiable(pred, mask_out)
+        return pred, mask_out, loss
+
+    @staticmethod
+    def backward(ctx, _dpred, _dmask, _dtoken):
+        gs: GraphedStep = ctx.gs
+        k = len(gs.gbs) - 1
+        gs.gbs[k].replay()
+        _lib.lib().cris_add_launch_count(gs.n_bwds[k])
+        return (None, None, None, None, *[gs.grad_of_name[n] for n in gs.seg_names[k]])
+
+
+class _GraphSeg(torch.autograd.Function):
+    """Segmented backward, link k < K-1: identity on the loss token in the forward; the backward replays backward
+    range k (range 0 = loss head + last layers) and hands its parameters' gradients to autograd — and therefore
+    to DistributedDataParallel's bucket all-reduce — before the remaining ranges run."""
+
+    @staticmethod
+    def forward(ctx, gs: GraphedStep, k: int, token, *params):
+        ctx.gs, ctx.k = gs, k
+        return token.view_as(token)
+
+    @staticmethod
+    def backward(ctx, dtoken):
+        gs: GraphedStep = ctx.gs
+        k = ctx.k
+        if k == 0:
+            gs.g.copy_(dtoken.detach().float().reshape(1))
+        gs.gbs[k].replay()
+        _lib.lib().cris_add_launch_count(gs.n_bwds[k])
+        return (None, None, dtoken, *[gs.grad_of_name[n] for n in gs.seg_names[k]])
+
+
 class Run:
     """State of one forward (+ backward) pass."""
     # defaults for helpers that tests build without __init__
@@ -396,6 +470,7 @@ class Run:
     xslot = 0
     _zarena: Optional[torch.Tensor] = None
     _zoff = 0
+    bwd_pos = 0
 
     def __init__(self, engine: Engine, img, word, mask, training: bool, record: bool):
         self.e = engine
@@ -423,6 +498,8 @@ class Run:
         self.xslot = 0  # exchange site index inside this pass (forward sites, then backward sites)
         self._zarena: Optional[torch.Tensor] = None
         self._zoff = 0
+        self.touched: Dict[str, int] = {}
+        self.bwd_pos = 0
 
     # ---- small helpers -------------------------------------------------------------------------
     def new(self, rows, C, fp32=False, geom=None, zero=False, ld=None) -> Mat:
@@ -462,6 +539,7 @@ class Run:
 
     def pg(self, name) -> torch.Tensor:
         """fp32 gradient buffer of a parameter: a view of ONE zero-filled flat buffer (one memset per backward)."""
+        self.touched[name] = self.bwd_pos  # last backward-tape position that writes this gradient
         g = self.pgrad.get(name)
         if g is None:
             if not self.pgrad:
@@ -1284,17 +1362,34 @@ class Run:
 
     # =================================================================================================
     def backward(self, dloss: torch.Tensor, names: List[str]):
-        xf, t, B, Ho, Wo, C = self._head
-        g = dloss.detach().float().reshape(1).contiguous()
-        dl = self.f32(B * Ho * Wo)
-        dxf, _ = self.grad_slot(xf)
-        dt, _ = self.grad_slot(t)
-        dt.buf.zero_()
-        call("cris_dynconv_bce_bwd", xf.ptr, xf.ld, t.ptr, t.ld, self.pred.data_ptr(), self.mask_out.data_ptr(),
-             g.data_ptr(), dl.data_ptr(), dxf.ptr, dxf.ld, dt.ptr, dt.ld, B, Ho, Wo, C)
-        for fn in reversed(self.tape):
-            fn()
-        self.tape = []  # closures <-> Run form reference cycles; drop them so buffers are freed promptly
+        self.backward_range(dloss, 0, None)
+        return self.collect_grads(names)
+
+    def backward_range(self, dloss: Optional[torch.Tensor], i0: int, i1: Optional[int]):
+        """Run the backward closures with reversed-tape positions [i0, i1); position 0 is preceded by the loss head.
+        The whole backward is backward_range(dloss, 0, None); GraphedStep may capture it in several ranges so that
+        gradients of the late layers reach DistributedDataParallel while the early layers are still running."""
+        if i0 == 0:
+            xf, t, B, Ho, Wo, C = self._head
+            g = dloss.detach().float().reshape(1).contiguous()
+            dl = self.f32(B * Ho * Wo)
+            dxf, _ = self.grad_slot(xf)
+            dt, _ = self.grad_slot(t)
+            dt.buf.zero_()
+            call("cris_dynconv_bce_bwd", xf.ptr, xf.ld, t.ptr, t.ld, self.pred.data_ptr(), self.mask_out.data_ptr(),
+                 g.data_ptr(), dl.data_ptr(), dxf.ptr, dxf.ld, dt.ptr, dt.ld, B, Ho, Wo, C)
+            self._rtape = list(reversed(self.tape))
+            self.tape = []  # closures <-> Run form reference cycles; drop them so buffers are freed promptly
+        n = len(self._rtape)
+        i1 = n if i1 is None else min(i1, n)
+        for i in range(i0, i1):
+            self.bwd_pos = i
+            self._rtape[i]()
+            self._rtape[i] = None
+        if i1 >= n:
+            self._rtape = []
+
+    def collect_grads(self, names: List[str]):
         out = []
         for k in names:
             out.append(self.pgrad.get(k))

@@ -178,6 +178,41 @@ def test_training_reduces_loss_and_state_dict_roundtrip(tiny):
     assert all(out[k].shape == sd[k].shape and out[k].dtype == sd[k].dtype for k in sd)
 
 
+def test_segmented_backward_graphs_give_the_same_gradients(tiny, monkeypatch):
+    """CRIS_B200_BWD_SEGMENTS=3 captures the backward as three graphs chained through autograd (gradients of the
+    late layers are handed to DDP before the early layers run): same kernels, same gradients (fp32 atomics in the
+    split-K / statistics paths make the comparison 1e-4-close instead of bitwise)."""
+    cfg, sd, model = tiny
+    eng = model._get_engine()
+    img, word, mask = synth.make_inputs(2, 5, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    img, word, mask = img.cuda(), word.cuda(), mask.cuda()
+    model.train()
+    saved = {k: b.clone() for k, b in model.named_buffers()}
+    grads = {}
+    for K in ("1", "3"):
+        monkeypatch.setenv("CRIS_B200_BWD_SEGMENTS", K)
+        eng.graphs = {}
+        with torch.no_grad():
+            for k, b in model.named_buffers():
+                b.copy_(saved[k])
+        model.zero_grad()
+        pred, m, loss = model(img, word, mask)
+        (loss * 3.0).backward()
+        gs = next(iter(eng.graphs.values()))
+        assert len(gs.gbs) == int(K)
+        grads[K] = (float(loss), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    monkeypatch.delenv("CRIS_B200_BWD_SEGMENTS")
+    eng.graphs = {}
+    with torch.no_grad():
+        for k, b in model.named_buffers():
+            b.copy_(saved[k])
+    model.eval()
+    assert abs(grads["1"][0] - grads["3"][0]) < 1e-6
+    assert grads["1"][1].keys() == grads["3"][1].keys() and len(grads["1"][1]) > 100
+    for k, g1 in grads["1"][1].items():
+        assert rel(grads["3"][1][k], g1) < 1e-3, k
+
+
 def test_dropout_path_runs(tiny):
     """cfg.dropout = 0.1 (the yaml default): statistical check only — masks cannot match torch's Philox stream."""
     cfg, sd, _ = tiny
