@@ -289,6 +289,119 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long l
   }
 }
 
+// ---- 32-bit / magic-division variants of the two kernels above (CRIS_B200_FASTDIV=1, work < 2^31) ------------
+struct BnIndex {
+  FastDiv dG, dHW, dW;
+  unsigned G, hw, wp, hp;
+  // flat work index -> (row, 8-channel group); returns whether the row is an interior pixel
+  __device__ __forceinline__ bool decode(unsigned i, unsigned& r, unsigned& c) const {
+    r = dG.div(i);
+    c = (i - r * G) * 8u;
+    if (wp == 0u) return true;
+    const unsigned rr = r - dHW.div(r) * hw;
+    const unsigned h = dW.div(rr), w = rr - h * wp;
+    return (h >= 1u) && (h <= hp - 2u) && (w >= 1u) && (w <= wp - 2u);
+  }
+};
+
+__global__ void bn_apply_fast_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const __nv_bfloat16* __restrict__ resid, long long ldr,
+                                     __nv_bfloat16* __restrict__ y, long long ldy, unsigned total, int relu,
+                                     BnIndex ix) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r, c;
+    const bool in = ix.decode(i, r, c);
+    float v[8];
+    if (in) {
+      float sc[8], sh[8];
+      ld8(x + (long long)r * ldx + c, v);
+      ld8f(scale + c, sc);
+      ld8f(shift + c, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+      if (resid != nullptr) {
+        float rv[8];
+        ld8(resid + (long long)r * ldr + c, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += rv[k];
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    st8(y + (long long)r * ldy + c, v);
+  }
+}
+
+// coef = [A | B | K | shf] (4 x C floats, bn_bwd_coeffs_kernel): dx = A*dz + B*x + K, mask = fma(x, A, shf) > 0
+__global__ void bn_bwd_coeffs_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ sums, float inv_count, float* __restrict__ coef,
+                                     int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float A = gamma[c] * invstd[c];
+  const float B = -A * invstd[c] * sums[C + c] * inv_count;
+  coef[c] = A;
+  coef[C + c] = B;
+  coef[2 * C + c] = -A * sums[c] * inv_count - B * mean[c];
+  coef[3 * C + c] = beta[c] - mean[c] * A;
+}
+
+__global__ void bn_bwd_apply_fast_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                         const __nv_bfloat16* __restrict__ y, long long ldy,
+                                         const __nv_bfloat16* __restrict__ x, long long ldx,
+                                         const float* __restrict__ coef, int C, __nv_bfloat16* __restrict__ dx,
+                                         long long lddx, __nv_bfloat16* __restrict__ dres, long long lddres,
+                                         int dres_accumulate, unsigned total, int relu, BnIndex ix) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r, c;
+    const bool in = ix.decode(i, r, c);
+    float o[8], dz[8];
+    if (in) {
+      float xv[8], A[8], Bc[8], Kc[8];
+      ld8(dy + (long long)r * lddy + c, dz);
+      ld8(x + (long long)r * ldx + c, xv);
+      ld8f(coef + c, A);
+      ld8f(coef + C + c, Bc);
+      ld8f(coef + 2 * C + c, Kc);
+      if (relu) {
+        if (y != nullptr) {
+          float yv[8];
+          ld8(y + (long long)r * ldy + c, yv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) dz[k] = 0.f;
+        } else {
+          float shf[8];
+          ld8f(coef + 3 * C + c, shf);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (!(fmaf(xv[k], A[k], shf[k]) > 0.f)) dz[k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], dz[k], fmaf(Bc[k], xv[k], Kc[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = dz[k] = 0.f;
+    }
+    st8(dx + (long long)r * lddx + c, o);
+    if (dres != nullptr) {
+      if (dres_accumulate) {
+        float old[8];
+        ld8(dres + (long long)r * lddres + c, old);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dz[k] += old[k];
+      }
+      st8(dres + (long long)r * lddres + c, dz);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, C % 128 == 0, C <= 2048.  y = xhat*gamma+beta (bf16 or fp32),
 // optional y2 = y + add[row % add_period] (bf16) — the "+ positional encoding" copy fed to q/k.
@@ -670,10 +783,34 @@ int cris_bn_coeffs(const float* sums, double count, const float* gamma, const fl
   return 0;
 }
 
+static bool fastdiv_enabled() {
+  const char* e = getenv("CRIS_B200_FASTDIV");  // read per call: tests flip it; default off until measured
+  return e != nullptr && e[0] == '1';
+}
+
+static BnIndex make_bn_index(int C, int hp, int wp) {
+  BnIndex ix;
+  ix.G = (unsigned)(C / 8);
+  ix.hp = (unsigned)(hp > 0 ? hp : 0);
+  ix.wp = (unsigned)(wp > 0 ? wp : 0);
+  ix.hw = ix.hp * ix.wp;
+  ix.dG = FastDiv(ix.G);
+  ix.dHW = FastDiv(ix.hw ? ix.hw : 1);
+  ix.dW = FastDiv(ix.wp ? ix.wp : 1);
+  return ix;
+}
+
 int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift, const void* resid, int64_t ldr,
                   void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0, "bn_apply: C=%d must be a multiple of 8", C);
   const long long work = rows * (C / 8);
+  if (fastdiv_enabled() && work < (1ll << 31) && rows < (1ll << 31)) {
+    bn_apply_fast_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, scale, shift, reinterpret_cast<const __nv_bfloat16*>(resid), ldr,
+        reinterpret_cast<__nv_bfloat16*>(y), ldy, (unsigned)work, relu, make_bn_index(C, hp, wp));
+    CRIS_LAUNCH_OK();
+    return 0;
+  }
   bn_apply_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, scale, shift, reinterpret_cast<const __nv_bfloat16*>(resid), ldr,
       reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, relu, hp, wp);
@@ -687,11 +824,37 @@ int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, 
                       int dres_accumulate, int64_t rows, int C, int relu, int hp, int wp, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   const long long work = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (fastdiv_enabled() && work < (1ll << 31) && rows < (1ll << 31)) {
+    // per-channel coefficients once (a [4, C] scratch vector owned by the library, stream-ordered reuse)
+    static float* coef = nullptr;
+    static int coef_cap = 0;
+    static int coef_dev = -1;
+    int dev = 0;
+    CRIS_CUDA_OK(cudaGetDevice(&dev));
+    if (coef == nullptr || coef_cap < C || coef_dev != dev) {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &st);
+      CRIS_CHECK_ARG(st == cudaStreamCaptureStatusNone, "bn_bwd_apply: coefficient scratch must be sized before capture");
+      if (coef != nullptr && coef_dev == dev) cudaFree(coef);
+      coef_cap = C > 4096 ? C : 4096;
+      CRIS_CUDA_OK(cudaMalloc(&coef, (size_t)4 * coef_cap * sizeof(float)));
+      coef_dev = dev;
+    }
+    bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, s>>>(mean, invstd, gamma, beta, sums, (float)(1.0 / count), coef, C);
+    CRIS_LAUNCH_OK();
+    bn_bwd_apply_fast_kernel<<<grid_for(work, 256), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), ldy,
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, coef, C, reinterpret_cast<__nv_bfloat16*>(dx), lddx,
+        reinterpret_cast<__nv_bfloat16*>(dres), lddres, dres_accumulate, (unsigned)work, relu, make_bn_index(C, hp, wp));
+    CRIS_LAUNCH_OK();
+    return 0;
+  }
+  bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, reinterpret_cast<const __nv_bfloat16*>(y), ldy,
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, mean, invstd, gamma, beta, sums, (float)(1.0 / count),
-      reinterpret_cast<__nv_bfloat16*>(dx), lddx, reinterpret_cast<__nv_bfloat16*>(dres), lddres, dres_accumulate,
-      rows, C, relu, hp, wp);
+      reinterpret_cast<__nv_bfloat16*>(dx), lddx, reinterpret_cast<__nv_bfloat16*>(dres), lddres, dres_accumulate, rows, C,
+      relu, hp, wp);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -130,6 +130,15 @@ def test_conv_bn_train(k, cin, cout, resid, relu):
     assert rel(run.Bf["bn.running_var"].cpu(), exp_rv) < 1e-2
 
 
+@pytest.mark.parametrize("k,cin,cout,resid,relu", [(1, 64, 128, False, True), (1, 128, 256, True, True),
+                                                   (3, 130, 64, False, False), (3, 32, 24, False, True)])
+def test_conv_bn_train_magic_division_kernels(monkeypatch, k, cin, cout, resid, relu):
+    """Same checks through the flag-gated BatchNorm apply kernels (32-bit indices, multiply-shift division,
+    per-channel backward coefficients precomputed): CRIS_B200_FASTDIV=1."""
+    monkeypatch.setenv("CRIS_B200_FASTDIV", "1")
+    test_conv_bn_train(k, cin, cout, resid, relu)
+
+
 def test_conv_bn_eval_and_bias_conv():
     g = torch.Generator().manual_seed(5)
     N, H, W, cin, cout = 2, 9, 11, 64, 64
