@@ -864,8 +864,18 @@ class Run:
                 self.ew(0, Mat(dy.buf, dy.rows, wpad, dy.ld, True, ptr=dy.ptr), None, Mat(t.buf, t.rows, wpad, wpad))
                 dy = t
             if bname:
-                sm = self.col_sum(dy, n_out)
-                self.pg(bname)[r0:r1].copy_(sm[:n_out])
+                if os.environ.get("CRIS_B200_BIAS_MMA", "0") == "1" and dy.rows >= 1024 and n_out % 8 == 0:
+                    # bias gradient on the tensor cores: 1^T . dy as an M = 1 GEMM (the ones vector is the only
+                    # in-bounds row of the A box, TMA zero-fills the other 127); split-K atomics land directly in
+                    # the zero-filled gradient buffer: one launch instead of reduce + finalize + two copies
+                    kp = _r8(dy.rows)
+                    ones = self.e.const(("ones_bf16", kp), lambda: torch.ones(1, kp, dtype=torch.bfloat16), self.dev)
+                    gbv = self.pg(bname)
+                    dst = Mat(gbv, 1, n_out, fp32=True, ptr=gbv.data_ptr() + 4 * r0)
+                    self.gemm(Mat(ones, 1, dy.rows, ld=kp), dy, dst, 1, n_out, dy.rows, b_mn=1, splits=0, accumulate=1)
+                else:
+                    sm = self.col_sum(dy, n_out)
+                    self.pg(bname)[r0:r1].copy_(sm[:n_out])
             gw = self.pg(wname)
             if transposed_weight:
                 gwm = Mat(gw, n_in, n_out, fp32=True)

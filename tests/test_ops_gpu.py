@@ -171,9 +171,9 @@ def test_conv_bn_eval_and_bias_conv():
 
 
 @pytest.mark.parametrize("act,transposed,n_out", [(0, False, 192), (1, False, 256), (0, True, 128), (0, False, 577)])
-def test_linear(act, transposed, n_out):
+def test_linear(act, transposed, n_out, rows=300):
     g = torch.Generator().manual_seed(11 + n_out)
-    rows, n_in = 300, 128
+    n_in = 128
     x = _bf(torch.randn(rows, n_in, generator=g))
     w = torch.randn(n_in, n_out, generator=g) * 0.1 if transposed else torch.randn(n_out, n_in, generator=g) * 0.1
     b = None if transposed else torch.randn(n_out, generator=g)
@@ -199,6 +199,14 @@ def test_linear(act, transposed, n_out):
     assert rel(run.pgrad["w"].cpu(), wr.grad) < 2e-2
     if br is not None:
         assert rel(run.pgrad["b"].cpu(), br.grad) < 1e-2
+
+
+@pytest.mark.parametrize("act,n_out,rows", [(0, 192, 5000), (1, 256, 4099), (0, 2048, 1500)])
+def test_linear_bias_gradient_on_tensor_cores(monkeypatch, act, n_out, rows):
+    """CRIS_B200_BIAS_MMA=1: the bias gradient is computed as an M=1 split-K GEMM (ones^T . dy) accumulating
+    straight into the parameter-gradient buffer; same tolerances as the column-reduction path."""
+    monkeypatch.setenv("CRIS_B200_BIAS_MMA", "1")
+    test_linear(act, False, n_out, rows)
 
 
 @pytest.mark.parametrize("C,x_fp32,with_add,rows", [(512, True, True, 130), (128, False, False, 130),
