@@ -99,8 +99,22 @@ def build_selftest() -> Path:
     return out
 
 
+def build_halo_probe() -> Path:
+    """tests/native/halo_probe: round-2 experiment (row-shifted UMMA descriptors on one swizzled TMA tile)."""
+    src = REPO / "tests" / "native" / "halo_probe.cu"
+    out = REPO / "tests" / "native" / "halo_probe"
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-I", str(REPO / "include"),
+           str(src), "-o", str(out), "-lcuda"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"halo_probe build failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     p = build_library(force="--force" in sys.argv, verbose=True)
     print(p)
     if "--selftest" in sys.argv:
         print(build_selftest())
+    if "--halo-probe" in sys.argv:
+        print(build_halo_probe())
