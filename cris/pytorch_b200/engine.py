@@ -471,6 +471,7 @@ class Run:
     _zarena: Optional[torch.Tensor] = None
     _zoff = 0
     bwd_pos = 0
+    touched: Optional[Dict[str, int]] = None
 
     def __init__(self, engine: Engine, img, word, mask, training: bool, record: bool):
         self.e = engine
@@ -539,6 +540,8 @@ class Run:
 
     def pg(self, name) -> torch.Tensor:
         """fp32 gradient buffer of a parameter: a view of ONE zero-filled flat buffer (one memset per backward)."""
+        if self.touched is None:
+            self.touched = {}
         self.touched[name] = self.bwd_pos  # last backward-tape position that writes this gradient
         g = self.pgrad.get(name)
         if g is None:

@@ -70,3 +70,51 @@ def test_engine_host_logic(monkeypatch, training):
             assert p.grad is None
         else:
             assert p.grad is not None and p.grad.shape == p.shape, k
+
+
+def test_hand_built_run_drives_single_ops(monkeypatch):
+    """tests/test_ops_gpu.py drives single building blocks through a `Run` created WITHOUT __init__ (its _mk_run
+    helper sets only a handful of attributes).  Every attribute those code paths read must therefore have a
+    class-level default: this CPU dry-run builds the same bare Run and walks conv+BN, linear, LayerNorm, residual
+    dropout, pooling and attention forward + backward with stubbed launches."""
+    rec = _Recorder()
+    monkeypatch.setattr(eng_mod, "call", rec.call)
+    monkeypatch.setattr(eng_mod, "gemm", rec.gemm)
+    monkeypatch.setattr(_lib, "device_check", lambda: None)
+    E = eng_mod
+    g = torch.Generator().manual_seed(0)
+    P = {"c1.weight": torch.randn(64, 32, 3, 3, generator=g), "bn.weight": torch.ones(64), "bn.bias": torch.zeros(64),
+         "w": torch.randn(128, 64, generator=g), "b": torch.zeros(128),
+         "ln.weight": torch.ones(128), "ln.bias": torch.zeros(128)}
+    Bf = {"bn.running_mean": torch.zeros(64), "bn.running_var": torch.ones(64),
+          "bn.num_batches_tracked": torch.zeros((), dtype=torch.long)}
+    r = object.__new__(E.Run)           # exactly the attribute set of tests/test_ops_gpu.py::_mk_run
+    r.e = E.Engine.bare()
+    r.dev = torch.device("cpu")
+    r.training, r.record = True, True
+    r.tape, r.pgrad = [], {}
+    r.P, r.Bf = P, Bf
+    r.p_drop = 0.1
+    r.seed_base, r.n_seed = 1234567, 0
+    r.seed_dev = None
+    r.world, r.sync_bn = 1, False
+    N, H, W = 2, 8, 8
+    x = r.padded(N, H, W, 32, zero=True)
+    y = r.conv_bn(x, "c1.weight", "bn", 3, relu=True)
+    pooled = r.avgpool(y)
+    up = r.upsample(pooled)
+    assert up.geom == (N, H, W)
+    tok = r.new(N * H * W, 64)
+    lin = r.linear(tok, "w", "b")
+    ln, _ = r.layernorm(lin, "ln")
+    res = r.residual_add(r.new(ln.rows, 128, True), ln, 0.1)
+    q = r.new(N * 16, 128)
+    att = r.attention(q, q, q, N, 2, 16, 16, p_drop=0.1)
+    for m in (up, res, att):
+        slot, _ = r.grad_slot(m)
+    n_fwd = len(rec.calls)
+    for fn in reversed(r.tape):
+        fn()
+    assert len(rec.calls) > n_fwd + 10
+    for k in ("c1.weight", "bn.weight", "bn.bias", "w", "b", "ln.weight", "ln.bias"):
+        assert r.pgrad[k].shape == P[k].shape
