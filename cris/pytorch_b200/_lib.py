@@ -79,6 +79,7 @@ _SIGS = {
     "cris_dynconv_bce_fwd": "pqpqpiipppiiiip",
     "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
     "cris_adam_step": "piqddddddppp",
+    "cris_conv3x3_halo": "pqpqipqpiiiiip",
 }
 
 _lib = None

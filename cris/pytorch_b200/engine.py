@@ -756,9 +756,17 @@ class Run:
         if probe:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        self.gemm(x, wp, z, x.rows, cout, cin, bias=bias, mask_geom=x.geom,
-                  colstats=part.data_ptr() if stats else None, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE,
-                  taps=9 if k == 3 else 1, tap_off=offs, b_tap_k=cin_pad if k == 3 else 0)
+        if (k == 3 and bias is None and cin in (32, 64) and cout in (32, 64) and x.geom is not None and not as_matrix
+                and os.environ.get("CRIS_B200_HALO_CONV", "0") == "1"):
+            # experimental small-channel path (csrc/conv_halo.cu): one halo tile per 128*SUB output rows, the nine
+            # taps are descriptor offsets into it instead of nine L2 re-reads
+            N_, H_, W_ = x.geom
+            call("cris_conv3x3_halo", x.ptr, x.ld, wp.ptr, wp.ld, cin_pad, z.ptr, z.ld,
+                 part.data_ptr() if stats else None, N_, H_, W_, cin, cout)
+        else:
+            self.gemm(x, wp, z, x.rows, cout, cin, bias=bias, mask_geom=x.geom,
+                      colstats=part.data_ptr() if stats else None, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE,
+                      taps=9 if k == 3 else 1, tap_off=offs, b_tap_k=cin_pad if k == 3 else 0)
         if probe:
             ev1.record()
             self.e.probe_events.append((ev0, ev1))

@@ -251,6 +251,14 @@ int cris_adam_step(const void* table_dev, int n_tensors, long long n_chunks, dou
                    double eps, double weight_decay, double step, const float* grad_scale, const float* found_inf,
                    void* stream);
 
+/* ---- EXPERIMENTAL: 3x3 convolution for 32/64-channel layers through one "halo" tile per output tile (stem conv2 /
+ *      conv3, layer1 3x3 convs; model/clip.py:17-25,165-182).  Same result as cris_gemm in CRIS_TAP_ACCUM mode with
+ *      the border mask: z[r][co] = sum_tap sum_ci x[r + off_tap][ci] * w[co][tap][ci] on interior rows, 0 on border
+ *      rows; x, z padded NHWC bf16; w_packed = cris_pack_conv_weight layout [Cout][9][cin_pad]; optional BatchNorm
+ *      column statistics accumulated like cris_gemm's colstats (caller-zeroed [min(64, ceil(rows/128))][2][Cout]). */
+int cris_conv3x3_halo(const void* x, int64_t ldx, const void* w_packed, int64_t ldw, int cin_pad, void* z, int64_t ldz,
+                      float* colstats, int N, int H, int W, int Cin, int Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

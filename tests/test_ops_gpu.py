@@ -2,6 +2,8 @@
 math on the same bf16-rounded inputs.  Tolerances are relative L2 errors sized for bf16 storage."""
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -137,6 +139,31 @@ def test_conv_bn_train_magic_division_kernels(monkeypatch, k, cin, cout, resid, 
     per-channel backward coefficients precomputed): CRIS_B200_FASTDIV=1."""
     monkeypatch.setenv("CRIS_B200_FASTDIV", "1")
     test_conv_bn_train(k, cin, cout, resid, relu)
+
+
+@pytest.mark.skipif(os.environ.get("CRIS_B200_EXPERIMENTAL", "0") != "1",
+                    reason="experimental halo-tile convolution (csrc/conv_halo.cu): set CRIS_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 20, 18, 32, 32), (2, 20, 18, 32, 64), (3, 30, 30, 64, 64),
+                                            (1, 6, 208, 32, 64), (2, 104, 104, 64, 64)])
+def test_conv_halo_matches_gemm(monkeypatch, N, H, W, cin, cout):
+    """CRIS_B200_HALO_CONV=1 routes 32/64-channel 3x3 convolutions through the halo-tile kernel; output and
+    BatchNorm column statistics must equal the default implicit-GEMM path (same bf16 products, fp32 accumulation
+    in a different order: 1e-2 relative on z, 2e-2 on the statistics)."""
+    g = torch.Generator().manual_seed(N * 1000 + W)
+    x = _bf(torch.randn(N, cin, H, W, generator=g))
+    P = {"c.weight": torch.randn(cout, cin, 3, 3, generator=g) * 0.1}
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CRIS_B200_HALO_CONV", flag)
+        run = _mk_run(P)
+        xm = to_padded(run, x)
+        z, part, nt = run.conv(xm, "c.weight", 3, stats=True)
+        torch.cuda.synchronize()
+        outs[flag] = (out_t(z), part.clone().cpu().reshape(nt, 2, cout).sum(0))
+    ref = F.conv2d(x, _bf(P["c.weight"]), padding=1)
+    assert rel(outs["0"][0], ref) < 1e-2
+    assert rel(outs["1"][0], ref) < 1e-2
+    assert rel(outs["1"][1], outs["0"][1]) < 2e-2
 
 
 def test_conv_bn_eval_and_bias_conv():

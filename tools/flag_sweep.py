@@ -15,6 +15,7 @@ SETTINGS = [
     ("CRIS_B200_BIAS_MMA=1", {"CRIS_B200_BIAS_MMA": "1"}),
     ("CRIS_B200_FASTDIV=1 CRIS_B200_BIAS_MMA=1", {"CRIS_B200_FASTDIV": "1", "CRIS_B200_BIAS_MMA": "1"}),
     ("CRIS_B200_BWD_SEGMENTS=3", {"CRIS_B200_BWD_SEGMENTS": "3"}),
+    ("CRIS_B200_HALO_CONV=1 (unverified kernel)", {"CRIS_B200_HALO_CONV": "1"}),
     ("CRIS_B200_TORCH_ADAM=1", {"CRIS_B200_TORCH_ADAM": "1"}),
 ]
 
