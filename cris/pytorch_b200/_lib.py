@@ -80,6 +80,7 @@ _SIGS = {
     "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
     "cris_adam_step": "piqddddddppp",
     "cris_conv3x3_halo": "pqpqipqpiiiiip",
+    "cris_pack_conv_weight_dgrad": "ppiiip",
 }
 
 _lib = None

@@ -237,6 +237,19 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
     out[i] = f2bf(ci < Cin ? w[((long long)co * Cin + ci) * taps + t] : 0.f);
   }
 }
+// data-gradient weights of a 3x3 conv as a FORWARD conv operand: out[ci][t'][co] = w[co][ci][8 - t'] (taps mirrored,
+// channels transposed), bf16 [Cin][9][cout_pad] zero padded: dx = conv3x3(dz, out) (experimental halo path)
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                              int Cin, int cout_pad) {
+  const long long total = (long long)Cin * 9 * cout_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_pad);
+    const int t = (int)((i / cout_pad) % 9);
+    const int ci = (int)(i / ((long long)cout_pad * 9));
+    out[i] = f2bf(co < Cout ? w[((long long)co * Cin + ci) * 9 + (8 - t)] : 0.f);
+  }
+}
 // fp32 [rows][cols] -> bf16 [rows][ld] (zero padded), optional per-row scale
 __global__ void pack_matrix_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long rows,
                                    int cols, int ld) {
@@ -373,6 +386,13 @@ int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void*
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream) {
   pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
                                                                                              taps, cin_pad);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_conv_weight_dgrad(const float* w, void* out, int Cout, int Cin, int cout_pad, void* stream) {
+  CRIS_CHECK_ARG(w && out && cout_pad >= Cout, "pack_conv_weight_dgrad: bad argument");
+  pack_conv_weight_dgrad_kernel<<<grid_for((long long)Cin * 9 * cout_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
+                                                                                               cout_pad);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -790,6 +790,16 @@ class Run:
             if x.need_grad:
                 slot, acc = self.grad_slot(x)
                 n_in = min(cin, x.C)
+                if (k == 3 and not acc and n_in == cin and cin in (32, 64) and cout in (32, 64) and x.geom is not None
+                        and not as_matrix and os.environ.get("CRIS_B200_HALO_CONV", "0") == "1"):
+                    # experimental: dx = conv3x3(dz, mirrored / transposed weights) through the halo-tile kernel
+                    cop = _r8(cout)
+                    wt = self.new(cin, 9 * cop)
+                    call("cris_pack_conv_weight_dgrad", self.P[wname].data_ptr(), wt.ptr, cout, cin, cop)
+                    N_, H_, W_ = x.geom
+                    call("cris_conv3x3_halo", dz.ptr, dz.ld, wt.ptr, wt.ld, cop, slot.ptr, slot.ld, None, N_, H_, W_,
+                         cout, cin)
+                    return
                 self.gemm(dz, wp, slot, x.rows, n_in, cout, b_mn=1, mask_geom=x.geom, resid=slot if acc else None,
                           tap_mode=TAP_ACCUM if k == 3 else TAP_NONE, taps=9 if k == 3 else 1,
                           tap_off=[-o for o in offs] if k == 3 else None, b_tap_n=cin_pad if k == 3 else 0,

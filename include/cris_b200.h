@@ -256,6 +256,9 @@ int cris_adam_step(const void* table_dev, int n_tensors, long long n_chunks, dou
  *      the border mask: z[r][co] = sum_tap sum_ci x[r + off_tap][ci] * w[co][tap][ci] on interior rows, 0 on border
  *      rows; x, z padded NHWC bf16; w_packed = cris_pack_conv_weight layout [Cout][9][cin_pad]; optional BatchNorm
  *      column statistics accumulated like cris_gemm's colstats (caller-zeroed [min(64, ceil(rows/128))][2][Cout]). */
+/* out[ci][t'][co] = w[co][ci][8 - t'] (bf16 [Cin][9][cout_pad]): the weights with which the data gradient of a 3x3
+ * convolution is itself a forward 3x3 convolution of dz, dx = cris_conv3x3_halo(dz, out) with Cin/Cout swapped */
+int cris_pack_conv_weight_dgrad(const float* w, void* out, int Cout, int Cin, int cout_pad, void* stream);
 int cris_conv3x3_halo(const void* x, int64_t ldx, const void* w_packed, int64_t ldw, int cin_pad, void* z, int64_t ldz,
                       float* colstats, int N, int H, int W, int Cin, int Cout, void* stream);
 

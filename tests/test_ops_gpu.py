@@ -153,17 +153,23 @@ def test_conv_halo_matches_gemm(monkeypatch, N, H, W, cin, cout):
     x = _bf(torch.randn(N, cin, H, W, generator=g))
     P = {"c.weight": torch.randn(cout, cin, 3, 3, generator=g) * 0.1}
     outs = {}
+    gz = _bf(torch.randn(N, cout, H, W, generator=g))
     for flag in ("0", "1"):
         monkeypatch.setenv("CRIS_B200_HALO_CONV", flag)
         run = _mk_run(P)
         xm = to_padded(run, x)
         z, part, nt = run.conv(xm, "c.weight", 3, stats=True)
-        torch.cuda.synchronize()
-        outs[flag] = (out_t(z), part.clone().cpu().reshape(nt, 2, cout).sum(0))
-    ref = F.conv2d(x, _bf(P["c.weight"]), padding=1)
-    assert rel(outs["0"][0], ref) < 1e-2
-    assert rel(outs["1"][0], ref) < 1e-2
+        set_grad(run, z, gz)
+        backward(run)
+        outs[flag] = (out_t(z), part.clone().cpu().reshape(nt, 2, cout).sum(0), out_t(run.grad_of(xm)))
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv2d(xr, _bf(P["c.weight"]), padding=1)
+    ref.backward(gz)
+    assert rel(outs["0"][0], ref.detach()) < 1e-2
+    assert rel(outs["1"][0], ref.detach()) < 1e-2
     assert rel(outs["1"][1], outs["0"][1]) < 2e-2
+    assert rel(outs["0"][2], xr.grad) < 2e-2
+    assert rel(outs["1"][2], xr.grad) < 2e-2
 
 
 def test_conv_bn_eval_and_bias_conv():
