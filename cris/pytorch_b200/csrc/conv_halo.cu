@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
             dp[j] = o;
           }
         }
-        if (p.colstats != nullptr) {
+        if (p.colstats != nullptr && (long long)tile * TM + sub * 128 < p.rows) {  // (partial rows exist per 128-row block)
           // per-column (sum, sumsq) of the stored (bf16-rounded) values over the warp's 32 rows: transposing
           // butterfly, lane L ends with column L; one atomic pair per lane into the tile's partial row
           float a[32], s2[32];
