@@ -98,7 +98,6 @@ def lib():
         L.cris_launch_count.restype = C.c_uint64
         L.cris_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
         L.cris_gemm.restype = C.c_int
-        L.cris_set_gemm_impl.argtypes = [C.c_int]
         L.cris_gemm_plan.argtypes = [C.POINTER(GemmArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.cris_add_launch_count.argtypes = [C.c_uint64]
         L.cris_add_launch_count.restype = None
@@ -121,7 +120,7 @@ def lib():
 
 def exported_symbols():
     """Every entry point include/cris_b200.h declares (used by the CPU 'library loads' test)."""
-    return ["cris_last_error", "cris_abi_version", "cris_device_check", "cris_set_gemm_impl", "cris_get_gemm_impl",
+    return ["cris_last_error", "cris_abi_version", "cris_device_check",
             "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_plan", "cris_gemm_args_size", "cris_gemm_args_last_offset",
             "cris_peer_buffer_bytes", "cris_peer_buffer_create", "cris_peer_buffer_open", "cris_peer_buffer_close",
             "cris_peer_allreduce_f32", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]

@@ -88,11 +88,12 @@ def build_selftest() -> Path:
     """tests/native/gemm_selftest: the pure-CUDA differential test of the GEMM core."""
     lib = build_library()
     src = REPO / "tests" / "native" / "gemm_selftest.cu"
+    ref = REPO / "tests" / "native" / "gemm_ref.cu"  # SIMT restatement: test-only, never part of the product library
     out = REPO / "tests" / "native" / "gemm_selftest"
-    if out.exists() and out.stat().st_mtime > max(src.stat().st_mtime, lib.stat().st_mtime):
+    if out.exists() and out.stat().st_mtime > max(src.stat().st_mtime, ref.stat().st_mtime, lib.stat().st_mtime):
         return out
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-I", str(REPO / "include"),
-           str(src), "-o", str(out), "-L", str(HERE), "-lcris_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cris/pytorch_b200"]
+           str(src), str(ref), "-o", str(out), "-L", str(HERE), "-lcris_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../cris/pytorch_b200"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"selftest build failed:\n{res.stdout}\n{res.stderr}")

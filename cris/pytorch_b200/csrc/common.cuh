@@ -46,6 +46,21 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     ::cris::count_launch();                                                             \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device).  The guard is an atomic bit set:
+// the forward thread and autograd-engine threads may reach the same call site concurrently (setting the attribute
+// twice is harmless, a torn plain bool is not defined behaviour), and the attribute is per-device state.
+#define CRIS_SET_SMEM_ONCE(kern, bytes)                                                              \
+  do {                                                                                               \
+    static std::atomic<unsigned long long> _done{0};                                                 \
+    int _dev = 0;                                                                                    \
+    cudaGetDevice(&_dev);                                                                            \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                             \
+    if (!(_done.load(std::memory_order_acquire) & _bit)) {                                           \
+      CRIS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));  \
+      _done.fetch_or(_bit, std::memory_order_release);                                               \
+    }                                                                                                \
+  } while (0)
+
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }

@@ -254,11 +254,7 @@ static int halo_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
 template <int CIN, int COUT, int SUB>
 static int launch_halo(const CUtensorMap& tmX, const CUtensorMap& tmW, HaloArgs p, int smem_bytes, cudaStream_t stream) {
   auto kern = conv_halo_kernel<CIN, COUT, SUB>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
+  CRIS_SET_SMEM_ONCE(kern, 227 * 1024);  // per instantiation and device
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

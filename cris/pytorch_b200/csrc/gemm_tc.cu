@@ -725,11 +725,7 @@ static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream
     kk.tma_store = 1;
   }
   auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, EPI>;
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  CRIS_SET_SMEM_ONCE(kern, Cfg::SMEM_BYTES);  // per template instantiation and device, thread-safe
   const int tiles_n = (a->N + BN - 1) / BN, tiles_m = (a->M + BM - 1) / BM;
   const long long total = (long long)tiles_n * tiles_m * a->batch * kk.taps_z * kk.splits;
   CRIS_CHECK_ARG(total < (1ll << 31), "GEMM has too many tiles");
@@ -768,9 +764,6 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
   return launch_tc_epi<BN, BK, A_MN, B_MN, EPI_PLAIN>(a, k, stream);
 }
 
-int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream);  // gemm_ref.cu
-
-static std::atomic<int> g_gemm_impl{0};
 static long long* g_trace = nullptr;  // debug timeline buffer (cris_debug_set_trace)
 
 int gemm_dispatch(const cris_gemm_args* a_in, cudaStream_t stream) {
@@ -791,7 +784,6 @@ int gemm_dispatch(const cris_gemm_args* a_in, cudaStream_t stream) {
   CRIS_CHECK_ARG(a->tap_mode != CRIS_TAP_WGRAD || (a->a_mn && a->b_mn), "wgrad tap mode needs MN-major A and B");
   CRIS_CHECK_ARG(a->tap_mode == CRIS_TAP_NONE || a->batch == 1, "tap modes are unbatched");
   CRIS_CHECK_ARG(a->batch_inner <= 1 || a->batch % a->batch_inner == 0, "batch must be a multiple of batch_inner");
-  if (g_gemm_impl.load() == 1) return gemm_ref_launch(a, stream);
 
   GemmKArgs k;
   k.M = a->M; k.N = a->N; k.K = a->K; k.nkb = 0;
@@ -857,7 +849,5 @@ int cris_gemm_plan(const cris_gemm_args* args, int* tile_n, int* splits) {
   }
   return 0;
 }
-void cris_set_gemm_impl(int impl) { cris::g_gemm_impl.store(impl); }
 void cris_debug_set_trace(void* dev_buf) { cris::g_trace = reinterpret_cast<long long*>(dev_buf); }
-int cris_get_gemm_impl(void) { return cris::g_gemm_impl.load(); }
 }

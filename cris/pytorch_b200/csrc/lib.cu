@@ -23,7 +23,7 @@ extern "C" {
 
 const char* cris_last_error(void) { return cris::g_err; }
 
-int cris_abi_version(void) { return 1; }
+int cris_abi_version(void) { return 2; }
 
 int cris_gemm_args_size(void) { return (int)sizeof(cris_gemm_args); }
 int cris_gemm_args_last_offset(void) { return (int)offsetof(cris_gemm_args, d_col_stride); }

@@ -219,12 +219,8 @@ int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt
                          float* pred, float* mask_out, float* loss_sum, int B, int H, int W, int C, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0 && 9 * C * 4 <= 96 * 1024, "dynconv: C=%d unsupported", C);
   CRIS_CHECK_ARG(mask == nullptr || (Hm % H == 0 && Wm % W == 0), "dynconv: mask %dx%d not an integer multiple", Hm, Wm);
-  static bool attr = false;
-  if (!attr) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
+  CRIS_SET_SMEM_ONCE(dynconv_bce_fwd_kernel<false>, 96 * 1024);
+  CRIS_SET_SMEM_ONCE(dynconv_bce_fwd_kernel<true>, 96 * 1024);
   dim3 grid((H * W + kDynPix - 1) / kDynPix, B);
   const float inv_n = 1.f / ((float)B * H * W);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -244,12 +240,8 @@ int cris_dynconv_bce_bwd(const void* x, int64_t ldx, const float* t, int64_t ldt
                          const float* target, const float* g, float* dl, void* dx, int64_t lddx, float* dt,
                          int64_t lddt, int B, int H, int W, int C, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0 && 9 * C * 4 <= 96 * 1024, "dynconv: C=%d unsupported", C);
-  static bool attr = false;
-  if (!attr) {
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CRIS_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
+  CRIS_SET_SMEM_ONCE(dynconv_bwd_x_kernel<false>, 96 * 1024);
+  CRIS_SET_SMEM_ONCE(dynconv_bwd_x_kernel<true>, 96 * 1024);
   const int npix = H * W;
   const float inv_n = 1.f / ((float)B * npix);
   bce_dlogit_kernel<<<dim3((npix + 255) / 256, B), 256, 0, STREAM>>>(pred, target, g, dl, dt, lddt, npix, C, inv_n);

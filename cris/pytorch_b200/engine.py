@@ -404,7 +404,9 @@ class _GraphFunction(torch.autograd.Function):
                 print(f"[hostprof] input copies {1e3 * (t1 - t0):.1f} ms, graph launch {1e3 * (t2 - t1):.1f} ms", flush=True)
         _lib.lib().cris_add_launch_count(gs.n_fwd)
         ctx.gs = gs
-        pred, mask_out, loss = gs.pred.detach(), gs.mask_out.detach(), gs.loss.detach().clone()
+        # fresh tensors: the static capture buffers are overwritten by the next replay, and callers may keep
+        # predictions / masks across iterations (metric accumulation), as they can with the reference
+        pred, mask_out, loss = gs.pred.detach().clone(), gs.mask_out.detach().clone(), gs.loss.detach().clone()
         ctx.mark_non_differentiable(pred, mask_out)
         return pred, mask_out, loss
 
@@ -429,7 +431,7 @@ class _GraphFirst(torch.autograd.Function):
         gs.gf.replay()
         _lib.lib().cris_add_launch_count(gs.n_fwd)
         ctx.gs = gs
-        pred, mask_out, loss = gs.pred.detach(), gs.mask_out.detach(), gs.loss.detach().clone()
+        pred, mask_out, loss = gs.pred.detach().clone(), gs.mask_out.detach().clone(), gs.loss.detach().clone()
         ctx.mark_non_differentiable(pred, mask_out)
         return pred, mask_out, loss
 

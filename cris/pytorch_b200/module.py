@@ -229,6 +229,14 @@ class CRIS(nn.Module):
         self.proj = proj
         if cfg.intermediate:
             raise NotImplementedError("cfg.intermediate=True is not used by any reference config")
+        # the attention kernels are written for 64-wide heads (every reference config: 512/8, 2048/32, 512/8);
+        # the reference derives head_dim = embed_dim // num_heads, so refuse anything else instead of mis-slicing
+        if cfg.vis_dim % cfg.num_head != 0 or cfg.vis_dim // cfg.num_head != 64:
+            raise ValueError(f"cris.pytorch_b200 needs vis_dim / num_head == 64 (got {cfg.vis_dim} / {cfg.num_head})")
+        tw = self.backbone.ln_final.weight.shape[0]
+        vw = self.backbone.visual.attnpool.q_proj.weight.shape[0]
+        if tw % 64 != 0 or vw % 64 != 0 or vw // self.backbone.visual.attnpool.num_heads != 64:
+            raise ValueError("cris.pytorch_b200 needs 64-wide attention heads in the CLIP text tower and attention pool")
         self.num_head = cfg.num_head
         self.dropout_p = float(cfg.dropout)
         self._engine = None

@@ -125,6 +125,9 @@ class Adam(torch.optim.Optimizer):
                                           found_inf.data_ptr() if found_inf is not None else None, _lib.stream_ptr())
                 if rc != 0:
                     raise RuntimeError(f"libcris_b200 cris_adam_step failed: {L.cris_last_error().decode()}")
+                # the kernel wrote the parameters through raw pointers: tell autograd / every version-keyed cache
+                # (engine.PackedWeights keeps bf16 copies keyed on p._version) that they changed in place
+                torch._C._increment_version(params)
         if found_inf is not None:
             # the flag travels to pinned host memory behind this step's kernels; reading it next time waits on that
             # copy's event only (a plain .item() would drain the whole stream, i.e. the next backward pass)

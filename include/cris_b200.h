@@ -31,9 +31,6 @@ extern "C" {
 const char* cris_last_error(void);          /* thread-local message of the last failure   */
 int  cris_abi_version(void);                /* bumped on any signature change             */
 int  cris_device_check(void);               /* 0 iff current device is sm_100 (B200)      */
-/* 0 = tcgen05 GEMM (product path), 1 = SIMT reference GEMM (differential testing only) */
-void cris_set_gemm_impl(int impl);
-int  cris_get_gemm_impl(void);
 /* debug: device buffer of 32*16 int64 receiving per-tile clock64 stamps of CTA 0 of every following GEMM (NULL = off) */
 void cris_debug_set_trace(void* dev_buf);
 uint64_t cris_launch_count(void);           /* kernels launched by this library so far    */

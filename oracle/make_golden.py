@@ -115,6 +115,13 @@ def run(arch: str, batch: int, size: int, tag: str, RefCRIS):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     RefCRIS = import_reference()
-    run("tiny", 2, 128, "tiny_b2_128", RefCRIS)
-    if "--tiny-only" not in sys.argv:
-        run("r50", 2, 416, "r50_b2_416", RefCRIS)
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    cases = [("tiny", 2, 128, "tiny_b2_128"), ("r50", 2, 416, "r50_b2_416"),
+             # round 2: the batch the SyncBN/DDP equivalence test shards over two ranks, and the r101 config
+             ("r50", 8, 416, "r50_b8_416"), ("r101", 2, 416, "r101_b2_416")]
+    for arch, b, size, tag in cases:
+        if only and tag not in only:
+            continue
+        if "--tiny-only" in sys.argv and arch != "tiny":
+            continue
+        run(arch, b, size, tag, RefCRIS)

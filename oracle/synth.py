@@ -172,11 +172,13 @@ def head_state_dict(cfg, seed: int = 1) -> Dict[str, torch.Tensor]:
     _conv(sd, g, "proj.vis.4.weight", c, c, 1, gain=1.0)
     sd["proj.vis.4.bias"] = g.normal(c, std=0.02)
     # small dynamic kernels keep the logits O(1) and centred near the 0.35 threshold
-    sd["proj.txt.weight"] = g.normal(c * 9 + 1, cfg.word_dim, std=0.35 / math.sqrt(cfg.word_dim * c * 9))
+    # r101 (word_dim 512): 4x the kernel scale, otherwise the logits' spread (sigma 0.07) sits inside the +-0.05 band
+    gain = 4.0 if (cfg.vis_dim, cfg.word_dim) == (512, 512) else 1.0
+    sd["proj.txt.weight"] = g.normal(c * 9 + 1, cfg.word_dim, std=gain * 0.35 / math.sqrt(cfg.word_dim * c * 9))
     sd["proj.txt.bias"] = g.normal(c * 9 + 1, std=0.002)
     # centre the eval logits on the mask threshold sigmoid(l) > 0.35 <=> l > -0.619 so that thresholded-mask /
     # IoU comparisons are not vacuous; offsets measured once per arch with these seeds
-    sd["proj.txt.bias"][-1] = {512: 0.10, 128: -0.52}.get(cfg.vis_dim, 0.10)
+    sd["proj.txt.bias"][-1] = {(512, 1024): 0.10, (512, 512): -0.435, (128, 128): -0.52}.get((cfg.vis_dim, cfg.word_dim), 0.10)
     return sd
 
 

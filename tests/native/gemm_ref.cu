@@ -1,8 +1,7 @@
 // gemm_ref.cu — SIMT restatement of cris_gemm (same argument semantics, one thread per output
-// element).  It exists for DIFFERENTIAL TESTING of the tcgen05 kernel on the GPU
-// (tests/native/gemm_selftest.cu, tests/test_gemm_gpu.py) and as a debugging aid
-// (cris_set_gemm_impl(1)); it is never selected by the product path.
-#include "common.cuh"
+// element).  TEST INFRASTRUCTURE: it is compiled only into tests/native/gemm_selftest (never into
+// libcris_b200.so) and exists for differential testing of the tcgen05 kernel on the GPU.
+#include "../../cris/pytorch_b200/csrc/common.cuh"
 
 namespace cris {
 
@@ -101,7 +100,7 @@ __global__ void gemm_ref_colstats(const cris_gemm_args a) {
   atomicAdd(a.colstats + (size_t)(mt & 63) * 2 * a.N + a.N + n, s1);
 }
 
-int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream) {
+static int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream) {
   RefArgs r;
   r.a = *a;
   r.a_rows = a->a_rows > 0 ? a->a_rows : (a->a_mn ? a->K : a->M);
@@ -110,13 +109,17 @@ int gemm_ref_launch(const cris_gemm_args* a, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((a->N + 31) / 32, (a->M + 7) / 8, a->batch * taps_z);
   gemm_ref_kernel<<<grid, block, 0, stream>>>(r);
-  CRIS_LAUNCH_OK();
+  if (cudaGetLastError() != cudaSuccess) return -3;
   if (a->colstats) {
     dim3 g2((a->N + 127) / 128, (a->M + 127) / 128);
     gemm_ref_colstats<<<g2, 128, 0, stream>>>(*a);
-    CRIS_LAUNCH_OK();
+    if (cudaGetLastError() != cudaSuccess) return -3;
   }
   return 0;
 }
 
 }  // namespace cris
+
+extern "C" int cris_ref_gemm(const cris_gemm_args* args, void* stream) {
+  return cris::gemm_ref_launch(args, reinterpret_cast<cudaStream_t>(stream));
+}

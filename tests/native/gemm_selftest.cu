@@ -17,6 +17,8 @@
 
 #include "../../include/cris_b200.h"
 
+extern "C" int cris_ref_gemm(const cris_gemm_args* args, void* stream);  // tests/native/gemm_ref.cu (test-only SIMT restatement)
+
 #define CK(x)                                                                      \
   do {                                                                             \
     cudaError_t e = (x);                                                           \
@@ -271,17 +273,14 @@ static int run_case(const Case& cs) {
   setup(cs, b);
   cris_gemm_args a = b.args;
   // tcgen05 path
-  cris_set_gemm_impl(0);
   a.D = b.dD_tc; a.colstats = b.dS_tc;
   if (cris_gemm(&a, nullptr) != 0) { printf("  tc launch error: %s\n", cris_last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("  tc kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
   // SIMT restatement
-  cris_set_gemm_impl(1);
   a.D = b.dD_ref; a.colstats = b.dS_ref;
-  if (cris_gemm(&a, nullptr) != 0) { printf("  ref launch error: %s\n", cris_last_error()); return 1; }
+  if (cris_ref_gemm(&a, nullptr) != 0) { printf("  ref launch error\n"); return 1; }
   CK(cudaDeviceSynchronize());
-  cris_set_gemm_impl(0);
 
   const size_t n = b.d_elems;
   std::vector<float> tc(n), rf(n);

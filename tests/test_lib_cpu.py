@@ -20,7 +20,7 @@ def test_library_builds_and_exports_header_symbols():
     for sym in declared:
         assert hasattr(L, sym), f"{sym} declared in cris_b200.h but not exported"
     assert set(_lib.exported_symbols()) >= declared - {"cris_gemm_args"}
-    assert L.cris_abi_version() == 1
+    assert L.cris_abi_version() == 2
     assert L.cris_gemm_args_size() == C.sizeof(_lib.GemmArgs)
 
 
