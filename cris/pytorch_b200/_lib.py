@@ -135,15 +135,51 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- live per-launch timing (bench.py's per-class roofline table; eager launches only) ------------------------
+_prof = None       # None = off; else a list of [entry point, class tag, flop, event0, event1]
+prof_tag = None    # set by the engine around a launch: (class, algorithmic flop) of the next call
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> [(entry point, class, flop, milliseconds)] of every launch since profile_begin()."""
+    global _prof
+    rows, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [(n, c, f, e0.elapsed_time(e1)) for n, c, f, e0, e1 in rows]
+
+
+def _timed(name, fn):
+    global prof_tag
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    cls, flop = prof_tag if prof_tag is not None else (None, 0.0)
+    prof_tag = None
+    _prof.append([name, cls, flop, e0, e1])
+    return rc
+
+
 def call(name: str, *args):
     """Invoke an entry point on the current CUDA stream (appended as the last argument)."""
-    rc = getattr(lib(), name)(*args, stream_ptr())
+    if _prof is not None:
+        rc = _timed(name, lambda: getattr(lib(), name)(*args, stream_ptr()))
+    else:
+        rc = getattr(lib(), name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"libcris_b200 {name} failed: {lib().cris_last_error().decode()}")
 
 
 def gemm(args: GemmArgs):
-    rc = lib().cris_gemm(C.byref(args), stream_ptr())
+    if _prof is not None:
+        rc = _timed("cris_gemm", lambda: lib().cris_gemm(C.byref(args), stream_ptr()))
+    else:
+        rc = lib().cris_gemm(C.byref(args), stream_ptr())
     if rc != 0:
         raise RuntimeError(f"libcris_b200 cris_gemm failed: {lib().cris_last_error().decode()}")
 

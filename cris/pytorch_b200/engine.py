@@ -216,7 +216,7 @@ class Engine:
             # a NCCL call cannot be replayed from the forward/backward graphs
             graphs_ok = self.use_graphs and (not self.needs_sync_bn() or self.peer_exchange(img.device) is not None
                                              or os.environ.get("CRIS_B200_GRAPHS_DDP", "0") == "1")
-            if graphs_ok and self.debug_taps is None and self.probe_name is None:
+            if graphs_ok and self.debug_taps is None and self.probe_name is None and _lib._prof is None:
                 key = (tuple(img.shape), tuple(word.shape), tuple(mask.shape), img.device.index, float(model.dropout_p),
                        self._param_fingerprint())
                 gs = self.graphs.get(key)
@@ -234,7 +234,7 @@ class Engine:
             pred, mask_r, loss = _CRISFunction.apply(self, names, img, word, mask, *params)
             return pred, mask_r, loss
         if (not training and self.use_graphs and self.debug_taps is None and self.probe_name is None
-                and self.gemm_log is None and img.is_cuda):
+                and self.gemm_log is None and _lib._prof is None and img.is_cuda):
             key = (tuple(img.shape), tuple(word.shape), img.device.index, self._param_fingerprint())
             ge = self.eval_graphs.get(key)
             if ge is None:
@@ -474,6 +474,7 @@ class Run:
     _zoff = 0
     bwd_pos = 0
     touched: Optional[Dict[str, int]] = None
+    in_backward = False
 
     def __init__(self, engine: Engine, img, word, mask, training: bool, record: bool):
         self.e = engine
@@ -629,6 +630,10 @@ class Run:
             g.mask_hp, g.mask_wp = mask_geom[1] + 2, mask_geom[2] + 2
         g.colstats = colstats
         g.a_rows, g.b_rows, g.d_col_stride = a_rows, b_rows, d_col_stride
+        if _lib._prof is not None:
+            nt = taps if tap_mode else 1
+            cls = ("attention" if batch > 1 else "wgrad" if accumulate else "dgrad" if self.in_backward else "fwd")
+            _lib.prof_tag = ("gemm_" + cls, 2.0 * M * N * K * nt * batch)
         if self.e.gemm_log is not None:
             self.e.gemm_log.append((M, N, K, batch, a_mn, b_mn, taps if tap_mode else 1, tap_mode, splits, int(D.fp32),
                                     int(resid is not None), int(colstats is not None)))
@@ -1402,6 +1407,7 @@ class Run:
         """Run the backward closures with reversed-tape positions [i0, i1); position 0 is preceded by the loss head.
         The whole backward is backward_range(dloss, 0, None); GraphedStep may capture it in several ranges so that
         gradients of the late layers reach DistributedDataParallel while the early layers are still running."""
+        self.in_backward = True
         if i0 == 0:
             xf, t, B, Ho, Wo, C = self._head
             g = dloss.detach().float().reshape(1).contiguous()

@@ -6,6 +6,9 @@ import pytest
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if _HERE not in sys.path:  # shared helpers (tests/parity_util.py)
+    sys.path.insert(0, _HERE)
 
 
 def pytest_configure(config):
