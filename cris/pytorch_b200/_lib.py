@@ -73,6 +73,7 @@ _SIGS = {
     "cris_eot_scatter": "ppiqpiqiiip",
     "cris_elementwise": "ipiqpiqpiqqifupp",
     "cris_pack_conv_weight": "ppiiiip",
+    "cris_unpack_conv_wgrad": "ppiiiip",
     "cris_pack_matrix": "ppqiip",
     "cris_batch_reduce": "piqpqiiiip",
     "cris_small_matmul": "pppiiiiip",

@@ -205,7 +205,27 @@ __device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], c
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
   if constexpr (EPI == EPI_ACCUM) {
-    if (cx.row_in) {
+    if (flags & F_TMA) {
+      // split-K / wgrad accumulation as TMA reductions: registers (one row per lane) -> 64-byte-swizzled smem box
+      // [32 rows x 16 fp32] -> cp.reduce.async.bulk.tensor (.add): the L2 adds whole lines; rows >= M are clipped
+      // by the tensor map.  (Was: 32 scalar atomicAdd per lane per chunk, one L2 operation per element.)
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (lane == 0) ptx::bulk_wait_read0();  // the previous box has been read out of this buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ sw) << 4)) =
+              make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_reduce_add_4d(tmD, stg, cx.dcol + 16 * h, trow, b_in, b_out);
+          ptx::bulk_commit();
+        }
+      }
+    } else if (cx.row_in) {
       float* ap = reinterpret_cast<float*>(p.D) + cx.drow + ((flags & F_WGRAD) ? cx.ztap * p.d_tap_n : 0) +
                   (long long)cx.ncol0 * p.d_col_stride;
 #pragma unroll
@@ -717,10 +737,20 @@ static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream
   CUtensorMap tmD = tmA;
   const int desz = a->d_fp32 ? 4 : 2;
   kk.tma_store = 0;
-  if (EPI != EPI_ACCUM && !a->accumulate && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 && (a->ldd * desz) % 16 == 0 &&
-      (a->batch <= 1 || ((a->strideD * desz) % 16 == 0 && (bin <= 1 || (a->strideD2 * desz) % 16 == 0)))) {
+  const bool d_dense = (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 && (a->ldd * desz) % 16 == 0 &&
+                       (a->batch <= 1 || ((a->strideD * desz) % 16 == 0 && (bin <= 1 || (a->strideD2 * desz) % 16 == 0)));
+  if (EPI != EPI_ACCUM && !a->accumulate && d_dense) {
     rc = make_tmap(&tmD, a->D, a->N, a->M, a->ldd, a->batch, a->strideD, bin, a->strideD2, 64 / desz, 32,
                    CU_TENSOR_MAP_SWIZZLE_64B, desz);
+    if (rc) return rc;
+    kk.tma_store = 1;
+  }
+  if (EPI == EPI_ACCUM && a->accumulate && a->d_fp32 && d_dense && a->d_col_stride <= 1 &&
+      (a->tap_mode != CRIS_TAP_WGRAD || (a->d_tap_n % 4) == 0)) {
+    // fp32 accumulation through TMA reductions; wgrad taps are column blocks d_tap_n apart in the same rows
+    const long long inner = a->tap_mode == CRIS_TAP_WGRAD ? (long long)(a->taps - 1) * a->d_tap_n + a->N : a->N;
+    rc = make_tmap(&tmD, a->D, inner, a->M, a->ldd, a->batch, a->strideD, bin, a->strideD2, 16, 32,
+                   CU_TENSOR_MAP_SWIZZLE_64B, 4);
     if (rc) return rc;
     kk.tma_store = 1;
   }

@@ -237,6 +237,20 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
     out[i] = f2bf(ci < Cin ? w[((long long)co * Cin + ci) * taps + t] : 0.f);
   }
 }
+// weight gradient of a k x k conv from the wgrad GEMM's tap-blocked layout back to the reference's OIHW:
+// gw[co][ci][t] = acc[co][t][ci] (fp32; acc = [Cout][taps][cin_pad], the layout the TMA reductions of the wgrad
+// GEMM write with unit stride; model/clip.py:17-25 autograd of nn.Conv2d).  Reads are coalesced along ci.
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ gw, int Cout, int Cin,
+                                         int taps, int cin_pad) {
+  const long long total = (long long)Cout * taps * cin_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int t = (int)((i / cin_pad) % taps);
+    const int co = (int)(i / ((long long)cin_pad * taps));
+    if (ci < Cin) gw[((long long)co * Cin + ci) * taps + t] = acc[i];
+  }
+}
 // data-gradient weights of a 3x3 conv as a FORWARD conv operand: out[ci][t'][co] = w[co][ci][8 - t'] (taps mirrored,
 // channels transposed), bf16 [Cin][9][cout_pad] zero padded: dx = conv3x3(dz, out) (experimental halo path)
 __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
@@ -386,6 +400,13 @@ int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void*
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream) {
   pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
                                                                                              taps, cin_pad);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_unpack_conv_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int cin_pad, void* stream) {
+  CRIS_CHECK_ARG(acc && gw && cin_pad >= Cin && taps >= 1, "unpack_conv_wgrad: bad argument");
+  unpack_conv_wgrad_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(acc, gw, Cout, Cin, taps,
+                                                                                              cin_pad);
   CRIS_LAUNCH_OK();
   return 0;
 }

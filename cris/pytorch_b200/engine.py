@@ -789,8 +789,12 @@ class Run:
             gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
             splits = 0  # the library plans tile width and split-K together (whole waves of its persistent grid)
             if k == 3:
-                self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
-                          d_tap_n=1, d_col_stride=9, splits=splits, accumulate=1)
+                # the nine taps accumulate into a zeroed [cout][9][cin_pad] fp32 scratch with unit column stride (TMA
+                # reductions, csrc/gemm_tc.cu EPI_ACCUM), then one small kernel writes the reference's OIHW layout
+                acc = Mat(self.zeros_f32(cout * 9 * cin_pad), cout, 9 * cin_pad, fp32=True)
+                self.gemm(dz, x, acc, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
+                          d_tap_n=cin_pad, splits=splits, accumulate=1)
+                call("cris_unpack_conv_wgrad", acc.ptr, gw.data_ptr(), cout, w_cols, 9, cin_pad)
             else:
                 self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, splits=splits, accumulate=1)
             # dgrad: dx[row] = sum_tap dz[row - off_tap] * W_tap

@@ -202,6 +202,9 @@ int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void*
                      int out_fp32, int64_t ldo, int64_t rows, int C, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                      void* stream);
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream);
+/* wgrad accumulator [Cout][taps][cin_pad] fp32 (what the tap-mode wgrad GEMM reduces into with unit stride) ->
+ * the reference's OIHW gradient gw[co][ci][t] (autograd of nn.Conv2d, model/clip.py:17-25) */
+int cris_unpack_conv_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int cin_pad, void* stream);
 int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
 int cris_batch_reduce(const void* in, int in_fp32, int64_t ldin, float* out, int64_t ldo, int B, int T, int C,
                       int accumulate, void* stream);

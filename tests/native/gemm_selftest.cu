@@ -100,6 +100,10 @@ static std::vector<Case> make_cases() {
   { auto x = add("conv_wgrad_c256_c256", 256, 256, 6 * 28 * 28, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 28; x->wp = 28; x->d_fp32 = 1; x->accumulate = 1; x->splits = 4; }
   { auto x = add("conv_wgrad_auto_split", 256, 512, 8 * 26 * 26, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 26; x->wp = 26; x->d_fp32 = 1; x->accumulate = 1; x->splits = 0; }
   { auto x = add("tn_wgrad_lin_auto_split", 512, 640, 9000, 1, 1, 1); x->d_fp32 = 1; x->accumulate = 1; x->splits = 0; }
+  // TMA-reduction epilogue: partial last chunk (N % 32 != 0 -> scalar atomics for that chunk only), N % 4 != 0, M < 128
+  { auto x = add("conv_wgrad_c128_c72_partial_chunk", 128, 72, 3 * 10 * 12, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 10; x->wp = 12; x->d_fp32 = 1; x->accumulate = 1; x->splits = 2; x->cpu_check = 1; }
+  { auto x = add("tn_wgrad_lin_N514", 200, 514, 3000, 1, 1, 1); x->d_fp32 = 1; x->accumulate = 1; x->splits = 3; x->cpu_check = 1; }
+  { auto x = add("conv_wgrad_c64_c64_auto", 64, 64, 16 * 30 * 30, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 30; x->wp = 30; x->d_fp32 = 1; x->accumulate = 1; x->splits = 0; }
   { auto x = add("conv_wgrad_c32_c32", 32, 32, 2 * 30 * 30, 1, 1, 1); x->tap_mode = 2; x->taps = 9; x->hp = 30; x->wp = 30; x->d_fp32 = 1; x->accumulate = 1; x->splits = 3; }
   return c;
 }
@@ -357,7 +361,7 @@ static int run_case(const Case& cs) {
 }
 
 static void perf(int only = -1) {
-  struct P { const char* name; int M, N, K, taps, hp, wp, a_mn, b_mn; };
+  struct P { const char* name; int M, N, K, taps, hp, wp, a_mn, b_mn; };  // a_mn && b_mn && taps > 1: tap-mode wgrad
   const P ps[] = {
       {"lin 43264x512x512", 43264, 512, 512, 1, 0, 0, 0, 0},
       {"lin 43264x2048x512", 43264, 2048, 512, 1, 0, 0, 0, 0},
@@ -370,6 +374,11 @@ static void perf(int only = -1) {
       {"dgrad 43264x512x2048 (B MN)", 43264, 512, 2048, 1, 0, 0, 0, 1},
       {"wgrad 512x512x43264 (A,B MN)", 512, 512, 43264, 1, 0, 0, 1, 1},
       {"wgrad 256x512x719104 (A,B MN)", 256, 512, 719104, 1, 0, 0, 1, 1},
+      {"wgrad3x3 256x512 64x(106x106)", 256, 512, 64 * 106 * 106, 9, 106, 106, 1, 1},
+      {"wgrad3x3 512x512 64x(28x28)", 512, 512, 64 * 28 * 28, 9, 28, 28, 1, 1},
+      {"wgrad3x3 64x64 64x(106x106)", 64, 64, 64 * 106 * 106, 9, 106, 106, 1, 1},
+      {"wgrad1x1 2048x512 64x(15x15)", 2048, 512, 64 * 15 * 15, 1, 0, 0, 1, 1},
+      {"dgrad3x3 64x(106x106) 256->512", 64 * 106 * 106, 512, 256, 9, 106, 106, 0, 1},
   };
   int pi = -1;
   for (const P& q : ps) {
@@ -377,16 +386,20 @@ static void perf(int only = -1) {
     if (only >= 0 && pi != only) continue;
     cris_gemm_args a; memset(&a, 0, sizeof(a));
     a.M = q.M; a.N = q.N; a.K = q.K; a.batch = 1; a.alpha = 1.f; a.splits = 1; a.a_mn = q.a_mn; a.b_mn = q.b_mn;
-    a.taps = q.taps; a.tap_mode = q.taps > 1 ? 1 : 0;
-    if (q.taps > 1) { int t = 0; for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) a.tap_off[t++] = dy * q.wp + dx; a.b_tap_k = q.K; }
-    if (q.hp) { a.mask_hp = q.hp; a.mask_wp = q.wp; }
-    long long a_rows = q.a_mn ? q.K : q.M, a_cols = q.a_mn ? q.M : q.K;
-    long long b_rows = q.b_mn ? q.K : q.N, b_cols = (q.b_mn ? q.N : (long long)q.K * q.taps);
-    a.lda = a_cols; a.ldb = b_cols; a.ldd = q.N;
-    void *A, *B, *D;
     int wg = (q.a_mn && q.b_mn);
-    CK(cudaMalloc(&A, a_rows * a_cols * 2)); CK(cudaMalloc(&B, b_rows * b_cols * 2)); CK(cudaMalloc(&D, (size_t)q.M * q.N * (wg ? 4 : 2)));
-    CK(cudaMemset(A, 0x3c, a_rows * a_cols * 2)); CK(cudaMemset(B, 0x3c, b_rows * b_cols * 2)); CK(cudaMemset(D, 0, (size_t)q.M * q.N * (wg ? 4 : 2)));
+    a.taps = q.taps; a.tap_mode = q.taps > 1 ? (wg ? 2 : 1) : 0;
+    if (q.taps > 1) {
+      int t = 0; for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) a.tap_off[t++] = dy * q.wp + dx;
+      if (wg) a.d_tap_n = q.N; else if (q.b_mn) a.b_tap_n = q.N; else a.b_tap_k = q.K;
+    }
+    if (q.hp && !wg) { a.mask_hp = q.hp; a.mask_wp = q.wp; }
+    long long a_rows = q.a_mn ? q.K : q.M, a_cols = q.a_mn ? q.M : q.K;
+    long long b_rows = q.b_mn ? q.K : q.N, b_cols = (q.b_mn ? (long long)q.N * (wg ? 1 : q.taps) : (long long)q.K * q.taps);
+    const int dtaps = (wg && q.taps > 1) ? q.taps : 1;
+    a.lda = a_cols; a.ldb = b_cols; a.ldd = (long long)q.N * dtaps;
+    void *A, *B, *D;
+    CK(cudaMalloc(&A, a_rows * a_cols * 2)); CK(cudaMalloc(&B, b_rows * b_cols * 2)); CK(cudaMalloc(&D, (size_t)q.M * q.N * dtaps * (wg ? 4 : 2)));
+    CK(cudaMemset(A, 0x3c, a_rows * a_cols * 2)); CK(cudaMemset(B, 0x3c, b_rows * b_cols * 2)); CK(cudaMemset(D, 0, (size_t)q.M * q.N * dtaps * (wg ? 4 : 2)));
     a.A = A; a.B = B; a.D = D;
     if (wg) { a.d_fp32 = 1; a.accumulate = 1; a.splits = 0; }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

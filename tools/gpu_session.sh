@@ -1,0 +1,35 @@
+#!/bin/bash
+# One gpurun session: tests + bench + profiles; every part has its own timeout and log under gpurun_out/.
+# usage: tools/gpu_session.sh <tag> [parts...]   parts: selftest tests bench ncu_wgrad launches
+TAG=${1:-r02}; shift
+PARTS=${@:-"selftest tests bench"}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+for part in $PARTS; do
+  case $part in
+    selftest)
+      timeout 300 tests/native/gemm_selftest perf > gpurun_out/${TAG}_selftest_perf.log 2>&1
+      echo "[selftest perf] rc=$?"; grep PERF gpurun_out/${TAG}_selftest_perf.log | tail -20 ;;
+    tests)
+      CRIS_B200_EXPERIMENTAL=1 timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -rA -s \
+        > gpurun_out/${TAG}_tests.log 2>&1
+      echo "[tests] rc=$?"; grep -E "^(PASSED|FAILED|ERROR|SKIPPED)|passed|failed" gpurun_out/${TAG}_tests.log | tail -90 ;;
+    bench)
+      timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+      echo "[bench] rc=$?"; tail -c 6000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err ;;
+    benchq)
+      timeout 600 python bench.py --steps 10 --warmup 3 --no-incumbent --no-cpu-baseline > gpurun_out/${TAG}_benchq.json 2> gpurun_out/${TAG}_benchq.err
+      echo "[benchq] rc=$?"; tail -c 5000 gpurun_out/${TAG}_benchq.json; tail -5 gpurun_out/${TAG}_benchq.err ;;
+    ncu_wgrad)
+      for i in 11 12 14; do
+        timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -f \
+          -o gpurun_out/${TAG}_wgrad_perf$i tests/native/gemm_selftest perf $i > gpurun_out/${TAG}_ncu_wgrad$i.log 2>&1
+        echo "[ncu wgrad $i] rc=$?"
+      done ;;
+    launches)
+      timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py 64 > gpurun_out/${TAG}_launches.log 2>&1
+      echo "[launches] rc=$?"; python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
+      head -45 gpurun_out/${TAG}_launches_summary.txt ;;
+  esac
+done
