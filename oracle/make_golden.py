@@ -118,7 +118,7 @@ if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
     cases = [("tiny", 2, 128, "tiny_b2_128"), ("r50", 2, 416, "r50_b2_416"),
              # round 2: the batch the SyncBN/DDP equivalence test shards over two ranks, and the r101 config
-             ("r50", 8, 416, "r50_b8_416"), ("r101", 2, 416, "r101_b2_416")]
+             ("r50", 8, 416, "r50_b8_416"), ("r101", 4, 416, "r101_b4_416")]
     for arch, b, size, tag in cases:
         if only and tag not in only:
             continue

@@ -51,7 +51,8 @@ def main():
     scaler = torch.amp.GradScaler("cuda")                                                        # train.py:110
     img, word, mask = synth.make_inputs(batch, 0, args.input_size, args.word_len, synth.ARCHS[arch]["vocab"])
     loader = [(img, word, mask.squeeze(1)) for _ in range(2)]   # RefDataset yields (img, word_vec, mask[H,W])
-    before = {k: v.detach().clone() for k, v in list(model.module.named_parameters())[:4]}
+    before = {k: v.detach().clone() for k, v in list(model.module.named_parameters())[:5]
+              if k != "backbone.logit_scale"}   # never used by the forward: no gradient, no update
     args.epochs = 1
     t0 = time.time()
     train(loader, model, optimizer, scheduler, scaler, 1, args)   # engine/engine.py:17-88, two iterations

@@ -45,8 +45,9 @@ def group_of(name: str) -> str:
     return p[0]
 
 
-def gradient_report(named_grads, golden_grads):
-    """named_grads: {name: fp32 gradient tensor (any device)}; golden: {name: {norm, idx, val} | None}."""
+def gradient_report(named_grads, golden_grads, skip_prefixes=()):
+    """named_grads: {name: fp32 gradient tensor (any device)}; golden: {name: {norm, idx, val} | None}.
+    skip_prefixes: group / parameter-name prefixes left out of the per-block aggregates."""
     per, groups = {}, {}
     for k, gg in golden_grads.items():
         if gg is None:
@@ -61,6 +62,8 @@ def gradient_report(named_grads, golden_grads):
         if nref < 1e-7:  # analytically zero in the reference (e.g. attnpool.k_proj.bias)
             continue
         if "txt_proj.1" in k:  # BatchNorm1d over the batch: a sign function at B=2, chaotic by construction
+            continue
+        if any(group_of(k).startswith(p) or k.startswith(p) for p in skip_prefixes):
             continue
         G = groups.setdefault(group_of(k), {"n2": 0.0, "r2": 0.0, "dot": 0.0, "m2": 0.0, "s2": 0.0, "count": 0})
         G["n2"] += n * n

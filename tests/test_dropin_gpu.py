@@ -28,7 +28,7 @@ def test_reference_train_loop_and_latency_tool_run_on_the_dropin():
     line = next((ln for ln in r.stdout.splitlines() if ln.startswith("DROPIN ")), None)
     assert r.returncode == 0 and line is not None, (r.stdout[-2000:], r.stderr[-4000:])
     out = json.loads(line[len("DROPIN "):])
-    assert out["train_iters"] == 2 and out["params_changed"] == 4
+    assert out["train_iters"] == 2 and out["params_changed"] == 4, out
     assert out["pred_shape"] == [1, 1, 104, 104]
     assert 140 < out["n_params_M"] < 150      # cris_r50: 146.85 M trainable parameters
     assert out["latency_b1_ms"] < 50

@@ -32,7 +32,8 @@ def _summary(named_grads):
         f = g.detach().flatten()
         gen = torch.Generator().manual_seed(f.numel() % 100003)
         idx = torch.randint(0, f.numel(), (min(24, f.numel()),), generator=gen)
-        out[k] = {"norm": f.double().norm().float().cpu(), "idx": idx, "val": f[idx.to(f.device)].float().cpu()}
+        # plain Python numbers: the summary crosses a multiprocessing queue (no shared tensor storage to keep alive)
+        out[k] = {"norm": float(f.double().norm()), "val": f[idx.to(f.device)].double().cpu().tolist()}
     return out
 
 
@@ -98,7 +99,8 @@ def test_two_ranks_syncbn_ddp_equal_one_gpu_global_batch(golden_dir):
         n1, n2 = float(s["norm"]), float(multi[k]["norm"])
         if n1 < 1e-7:
             continue
-        sr = float((multi[k]["val"].double() - s["val"].double()).norm() / (s["val"].double().norm() + 1e-30))
+        a, b = torch.tensor(multi[k]["val"]), torch.tensor(s["val"])
+        sr = float((a - b).norm() / (b.norm() + 1e-30))
         if abs(n2 / n1 - 1.0) > 0.03 or sr > 0.06:
             bad.append((k, n2 / n1, sr))
     print(f"{len(bad)} of {len(single)} gradient tensors outside tolerance; worst: {sorted(bad, key=lambda t: -t[2])[:5]}")
