@@ -730,6 +730,22 @@ __global__ void __launch_bounds__(256) stats_finalize_bwd_kernel(const float* __
 
 }  // namespace cris
 
+namespace cris {  // bn_stream.cu: shared-memory-staged streaming versions of the three big BatchNorm passes
+bool bn_stream_ok(long long rows, int C, int hp, int wp);
+int bn_apply_stream(const void* x, long long ldx, const float* scale, const float* shift, const void* resid, long long ldr,
+                    void* y, long long ldy, long long rows, int C, int relu, int hp, int wp, cudaStream_t s);
+int bn_reduce_stream(int mode, const void* a0, long long lda, const void* y, long long ldy, const void* x, long long ldx,
+                     const float* mean, const float* invstd, const float* scale, const float* shift, long long rows, int C,
+                     int relu, int hp, int wp, float* partials, int n_part, cudaStream_t s);
+int bn_bwd_apply_stream(const void* dy, long long lddy, const void* y, long long ldy, const void* x, long long ldx,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta, const float* sums,
+                        double count, void* dx, long long lddx, void* dres, long long lddres, int dres_accumulate,
+                        long long rows, int C, int relu, int hp, int wp, cudaStream_t s);
+static bool al16(const void* p, long long ld) {
+  return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0);
+}
+}  // namespace cris
+
 using namespace cris;
 
 extern "C" {
@@ -742,6 +758,10 @@ int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void
   CRIS_CHECK_ARG(n_blocks >= 1, "col_reduce: n_blocks");
   ColReduceArgs p{a, lda, a_fp32, a2, lda2, y, ldy, x, ldx, x_fp32, mean, rstd, scale, shift, rows, C, relu, hp, wp, partials};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if ((mode == 0 || mode == 1) && !a_fp32 && !x_fp32 && a2 == nullptr && bn_stream_ok(rows, C, hp, wp) && al16(a, lda) &&
+      (mode == 0 || (x != nullptr && al16(x, ldx) && al16(y, ldy))))
+    return bn_reduce_stream(mode, a, lda, y, ldy, x, ldx, mean, rstd, scale, shift, rows, C, relu, hp, wp, partials,
+                            n_blocks < 64 ? n_blocks : 64, s);
   switch (mode) {
     case 0: col_reduce_kernel<0><<<n_blocks, 256, 0, s>>>(p); break;
     case 1: col_reduce_kernel<1><<<n_blocks, 256, 0, s>>>(p); break;
@@ -803,6 +823,9 @@ static BnIndex make_bn_index(int C, int hp, int wp) {
 int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift, const void* resid, int64_t ldr,
                   void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0, "bn_apply: C=%d must be a multiple of 8", C);
+  if (bn_stream_ok(rows, C, hp, wp) && al16(x, ldx) && al16(resid, ldr) && al16(y, ldy))
+    return bn_apply_stream(x, ldx, scale, shift, resid, ldr, y, ldy, rows, C, relu, hp, wp,
+                           reinterpret_cast<cudaStream_t>(stream));
   const long long work = rows * (C / 8);
   if (fastdiv_enabled() && work < (1ll << 31) && rows < (1ll << 31)) {
     bn_apply_fast_kernel<<<grid_for(work, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -825,6 +848,10 @@ int cris_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, 
   CRIS_CHECK_ARG(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   const long long work = rows * (C / 8);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn_stream_ok(rows, C, hp, wp) && al16(dy, lddy) && al16(y, ldy) && al16(x, ldx) && al16(dx, lddx) &&
+      al16(dres, lddres))
+    return bn_bwd_apply_stream(dy, lddy, y, ldy, x, ldx, mean, invstd, gamma, beta, sums, count, dx, lddx, dres, lddres,
+                               dres_accumulate, rows, C, relu, hp, wp, s);
   if (fastdiv_enabled() && work < (1ll << 31) && rows < (1ll << 31)) {
     // per-channel coefficients once (a [4, C] scratch vector owned by the library, stream-ordered reuse)
     static float* coef = nullptr;

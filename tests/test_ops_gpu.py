@@ -132,6 +132,88 @@ def test_conv_bn_train(k, cin, cout, resid, relu):
     assert rel(run.Bf["bn.running_var"].cpu(), exp_rv) < 1e-2
 
 
+@pytest.mark.parametrize("C,N,H,W,relu,with_y,strided", [(8, 4, 40, 30, True, False, False), (64, 8, 52, 52, True, True, False),
+                                                        (256, 8, 26, 26, True, True, True), (256, 8, 26, 26, False, False, True),
+                                                        (2048, 16, 13, 13, True, False, False), (1024, 3000, 0, 0, True, False, False)])
+def test_bn_stream_kernels_match_register_kernels(monkeypatch, C, N, H, W, relu, with_y, strided):
+    """The shared-memory-staged streaming BatchNorm passes (csrc/bn_stream.cu: bulk async copies + mbarrier pipeline)
+    against the register-streaming kernels they replace (csrc/norm.cu, CRIS_B200_BN_STREAM=0), through the C ABI on
+    realistic shapes: forward apply bit-exact (same arithmetic), statistics to fp32 summation order, backward apply
+    to one bf16 ulp (the coefficients are folded differently).  H == 0: a plain [N, C] matrix (BatchNorm1d)."""
+    from cris.pytorch_b200._lib import call
+    g = torch.Generator().manual_seed(C + N)
+    hp, wp = (H + 2, W + 2) if H else (0, 0)
+    rows = N * hp * wp if H else N
+    ld = C + 64 if strided else C
+
+    def mat(scale=1.0):
+        t = (torch.randn(rows, ld, generator=g) * scale).to(torch.bfloat16).cuda()
+        return t
+
+    z, resid, dy = mat(), mat(), mat()
+    scale = (torch.rand(C, generator=g) + 0.5).cuda()
+    shift = (torch.randn(C, generator=g) * 0.3).cuda()
+    mean = (torch.randn(C, generator=g) * 0.2).cuda()
+    invstd = (torch.rand(C, generator=g) + 0.5).cuda()
+    gamma = scale / invstd
+    beta = shift + mean * scale
+    res_ptr = resid.data_ptr() if with_y else None
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CRIS_B200_BN_STREAM", flag)
+        y = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        call("cris_bn_apply", z.data_ptr(), ld, scale.data_ptr(), shift.data_ptr(), res_ptr, ld, y.data_ptr(), ld, rows, C,
+             int(relu), hp, wp)
+        nb = max(1, min(592, rows // 64))
+        part = torch.zeros(min(nb, 64) * 2 * C, device="cuda")
+        ymask = y if (with_y or not relu) else None
+        call("cris_col_reduce", 1, dy.data_ptr(), ld, 0, None, 0, ymask.data_ptr() if ymask is not None else None,
+             ld if ymask is not None else 0, z.data_ptr(), ld, 0, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+             shift.data_ptr(), rows, C, int(relu), hp, wp, part.data_ptr(), nb)
+        part0 = torch.zeros(min(nb, 64) * 2 * C, device="cuda")
+        call("cris_col_reduce", 0, z.data_ptr(), ld, 0, None, 0, None, 0, None, 0, 0, None, None, None, None, rows, C, 0,
+             hp, wp, part0.data_ptr(), nb)
+        sums = part.reshape(-1, 2 * C).sum(0).contiguous()
+        count = float(N * H * W if H else N)
+        dz = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        dres = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        call("cris_bn_bwd_apply", dy.data_ptr(), ld, ymask.data_ptr() if ymask is not None else None,
+             ld if ymask is not None else 0, z.data_ptr(), ld, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+             beta.data_ptr(), sums.data_ptr(), count, dz.data_ptr(), ld, dres.data_ptr() if with_y else None, ld, 0, rows,
+             C, int(relu), hp, wp)
+        torch.cuda.synchronize()
+        out[flag] = (y[:, :C].float(), part.reshape(-1, 2 * C).sum(0), part0.reshape(-1, 2 * C).sum(0), dz[:, :C].float(),
+                     dres[:, :C].float() if with_y else None, y[:, C:].float())
+    a, b = out["0"], out["1"]
+    assert torch.equal(a[0], b[0])                       # forward apply: identical arithmetic
+    assert torch.equal(a[5], b[5])                       # columns beyond C (a concat neighbour's slice) untouched
+    assert rel(b[1], a[1]) < 1e-4 and rel(b[2], a[2]) < 1e-4
+    assert rel(b[3], a[3]) < 6e-3
+    if with_y:
+        assert torch.equal(a[4], b[4])
+    # and against plain fp32 math
+    zf = z[:, :C].float()
+    yr = zf * scale + shift + (resid[:, :C].float() if with_y else 0)
+    if relu:
+        yr = yr.clamp_min(0)
+    if H:
+        m = torch.zeros(N, hp, wp, dtype=torch.bool, device="cuda")
+        m[:, 1:-1, 1:-1] = True
+        m = m.reshape(-1, 1)
+    else:
+        m = torch.ones(rows, 1, dtype=torch.bool, device="cuda")
+    yr = torch.where(m, yr, torch.zeros_like(yr))
+    assert rel(b[0], yr) < 4e-3
+    dzm = dy[:, :C].float() * m
+    if relu:
+        dzm = dzm * ((b[0] > 0) if with_y else (zf * scale + shift > 0))
+    xh = (zf - mean) * invstd
+    s0, s1 = dzm.sum(0), (dzm * xh).sum(0)
+    assert rel(b[1][:C], s0) < 2e-3 and rel(b[1][C:], s1) < 2e-3
+    dxr = gamma * invstd * (dzm - s0 / count - xh * s1 / count) * m
+    assert rel(b[3], dxr) < 8e-3
+
+
 @pytest.mark.parametrize("k,cin,cout,resid,relu", [(1, 64, 128, False, True), (1, 128, 256, True, True),
                                                    (3, 130, 64, False, False), (3, 32, 24, False, True)])
 def test_conv_bn_train_magic_division_kernels(monkeypatch, k, cin, cout, resid, relu):

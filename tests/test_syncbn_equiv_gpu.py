@@ -7,10 +7,15 @@ On a box with >= 2 GPUs the ranks sit on different devices; on a single-GPU box 
 time-slices the two contexts; the NVLink peer-exchange kernels then hand over through the same IPC mapping), like
 tests/test_peer_gpu.py.  The process group is gloo so that the test does not depend on two NCCL devices.
 
-Tolerances: the two runs execute the same kernels on the same data, only the fp32 summation order of the BatchNorm
-statistics (rank-ordered partial sums vs one pass) and of the gradient average differs:
-  loss |delta| <= 2e-3; every gradient tensor: norm within 3 %, sampled values within 6 % (relative L2) for >= 97 %
-  of the tensors (a bf16 rounding flip that crosses a ReLU is the residual).
+What "equal" can mean here.  Activations are STORED in bf16: a perturbation of 1e-7 (the fp32 summation order of a
+BatchNorm statistic: rank-ordered partial sums, or merely the arrival order of fp32 atomics) flips a few bf16
+roundings, each flip is a 0.4 % change of one element, and within about four layers ANY two non-bit-identical
+executions differ by the bf16 rounding noise itself; downstream ReLU masks then differ in ~0.4 % of the units per
+layer.  So two runs of the SAME single-GPU configuration already disagree in the image tower's gradient direction
+(cosine 0.8-0.9, measured below as the run-to-run floor) while norms, the loss and every other block agree closely.
+The test therefore measures that floor (1x8 run twice) and requires the 2x4 SyncBN/DDP run to sit at it:
+  loss |delta| <= 2e-3 (and <= 3e-2 vs the fp32 reference); every gradient tensor's norm within 5 % for >= 97 % of
+  the tensors; per block, cosine(2x4, 1x8) >= cosine(1x8, 1x8') - 0.08 and >= 0.62 (image tower) / 0.92 (rest).
 """
 import os
 
@@ -20,7 +25,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import synth
-from parity_util import build
+from parity_util import build, group_of
 
 pytestmark = pytest.mark.gpu
 ARCH, B_GLOBAL, SIZE = "r50", 8, 416
@@ -33,7 +38,7 @@ def _summary(named_grads):
         gen = torch.Generator().manual_seed(f.numel() % 100003)
         idx = torch.randint(0, f.numel(), (min(24, f.numel()),), generator=gen)
         # plain Python numbers: the summary crosses a multiprocessing queue (no shared tensor storage to keep alive)
-        out[k] = {"norm": float(f.double().norm()), "val": f[idx.to(f.device)].double().cpu().tolist()}
+        out[k] = {"norm": float(f.double().norm()), "numel": f.numel(), "val": f[idx.to(f.device)].double().cpu().tolist()}
     return out
 
 
@@ -68,17 +73,38 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_ranks_syncbn_ddp_equal_one_gpu_global_batch(golden_dir):
-    # 1) one process, the whole batch
+def _group_cos(sa, sb):
+    """per-block cosine / norm ratio of two gradient summaries (samples weighted by tensor size)"""
+    G = {}
+    for k, a in sa.items():
+        if a["norm"] < 1e-7 or "txt_proj.1" in k:
+            continue
+        b = sb[k]
+        va, vb = torch.tensor(a["val"]), torch.tensor(b["val"])
+        w = a["numel"] / max(1, va.numel())
+        g = G.setdefault(group_of(k), [0.0, 0.0, 0.0, 0.0, 0.0])
+        g[0] += w * float(va @ vb); g[1] += w * float(va @ va); g[2] += w * float(vb @ vb)
+        g[3] += a["norm"] ** 2; g[4] += b["norm"] ** 2
+    return {k: {"cos": g[0] / ((g[1] * g[2]) ** 0.5 + 1e-30), "norm_ratio": (g[4] / g[3]) ** 0.5} for k, g in G.items()}
+
+
+def _single_run(seed_note=""):
     cfg, sd, model = build(ARCH)
     img, word, mask = synth.make_inputs(B_GLOBAL, 0, SIZE, cfg.word_len, synth.ARCHS[ARCH]["vocab"])
     model.train()
-    _, _, loss1 = model(img.cuda(), word.cuda(), mask.cuda())
-    loss1.backward()
-    single = _summary({k: p.grad for k, p in model.named_parameters() if p.grad is not None})
-    loss1 = float(loss1)
+    _, _, loss = model(img.cuda(), word.cuda(), mask.cuda())
+    loss.backward()
+    out = _summary({k: p.grad for k, p in model.named_parameters() if p.grad is not None}), float(loss)
     del model
     torch.cuda.empty_cache()
+    return out
+
+
+def test_two_ranks_syncbn_ddp_equal_one_gpu_global_batch(golden_dir):
+    # 1) one process, the whole batch — twice: the second run measures the run-to-run floor of a bf16-storage pass
+    single, loss1 = _single_run()
+    again, loss1b = _single_run()
+    floor = _group_cos(single, again)
     # 2) two ranks, half the batch each
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -92,28 +118,27 @@ def test_two_ranks_syncbn_ddp_equal_one_gpu_global_batch(golden_dir):
     assert all(r[1] == "ok" for r in res), res
     r0 = next(r for r in res if r[0] == 0)
     loss2, multi = r0[2], r0[3]
-    print(f"loss 1x8 {loss1:.6f}  2x4 {loss2:.6f}  peer exchange {r0[4]}  graphs {r0[5]}")
-    assert abs(loss1 - loss2) <= 2e-3
-    bad = []
-    for k, s in single.items():
-        n1, n2 = float(s["norm"]), float(multi[k]["norm"])
-        if n1 < 1e-7:
-            continue
-        a, b = torch.tensor(multi[k]["val"]), torch.tensor(s["val"])
-        sr = float((a - b).norm() / (b.norm() + 1e-30))
-        if abs(n2 / n1 - 1.0) > 0.03 or sr > 0.06:
-            bad.append((k, n2 / n1, sr))
-    print(f"{len(bad)} of {len(single)} gradient tensors outside tolerance; worst: {sorted(bad, key=lambda t: -t[2])[:5]}")
+    print(f"loss 1x8 {loss1:.6f} / {loss1b:.6f}  2x4 {loss2:.6f}  peer exchange {r0[4]}  graphs {r0[5]}")
+    assert abs(loss1 - loss2) <= 2e-3 and abs(loss1 - loss1b) <= 2e-3
+    bad = [(k, multi[k]["norm"] / s["norm"]) for k, s in single.items()
+           if s["norm"] >= 1e-7 and abs(multi[k]["norm"] / s["norm"] - 1.0) > 0.05]
+    print(f"{len(bad)} of {len(single)} gradient norms differ by more than 5 %: {bad[:5]}")
     assert len(bad) <= 0.03 * len(single), bad[:10]
+    got = _group_cos(single, multi)
+    for name in sorted(got):
+        print(f"  {name:34s} cos(2x4, 1x8) {got[name]['cos']:.3f}   run-to-run floor cos(1x8, 1x8') {floor[name]['cos']:.3f}"
+              f"   norm ratio {got[name]['norm_ratio']:.3f}")
+    for name, g in got.items():
+        lo = 0.62 if name.startswith("backbone.visual") else 0.92
+        assert g["cos"] >= lo and g["cos"] >= floor[name]["cos"] - 0.08, (name, g, floor[name])
+        assert 0.95 <= g["norm_ratio"] <= 1.05, (name, g)
     # 3) both agree with the unmodified reference at B=8
     g = torch.load(os.path.join(golden_dir, "r50_b8_416.pt"), weights_only=False)
     assert abs(loss2 - float(g["train_loss"])) <= 3e-2
-    groups_ok = 0
+    ok = total = 0
     for k, gg in g["grads"].items():
         if gg is None or float(gg["norm"]) < 1e-7 or "txt_proj.1" in k:
             continue
-        n2 = float(multi[k]["norm"])
-        if 0.5 <= n2 / float(gg["norm"]) <= 2.0:
-            groups_ok += 1
-    total = sum(1 for k, gg in g["grads"].items() if gg is not None and float(gg["norm"]) >= 1e-7 and "txt_proj.1" not in k)
-    assert groups_ok >= 0.95 * total, (groups_ok, total)
+        total += 1
+        ok += int(0.8 <= multi[k]["norm"] / float(gg["norm"]) <= 1.25)
+    assert ok >= 0.97 * total, (ok, total)
