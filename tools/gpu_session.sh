@@ -14,6 +14,10 @@ for part in $PARTS; do
       CRIS_B200_EXPERIMENTAL=1 timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -rA -s \
         > gpurun_out/${TAG}_tests.log 2>&1
       echo "[tests] rc=$?"; grep -E "^(PASSED|FAILED|ERROR|SKIPPED)|passed|failed" gpurun_out/${TAG}_tests.log | tail -90 ;;
+    tests_ops)
+      CRIS_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_parity_gpu.py -q --no-header -p no:cacheprovider -rA \
+        > gpurun_out/${TAG}_tests_ops.log 2>&1
+      echo "[tests_ops] rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_tests_ops.log | tail -30 ;;
     tests_new)
       timeout 1200 python -m pytest tests/test_parity_full_gpu.py tests/test_syncbn_equiv_gpu.py tests/test_dropin_gpu.py -q --no-header \
         -p no:cacheprovider -rA -s > gpurun_out/${TAG}_tests_new.log 2>&1
