@@ -74,6 +74,8 @@ _SIGS = {
     "cris_elementwise": "ipiqpiqpiqqifupp",
     "cris_pack_conv_weight": "ppiiiip",
     "cris_unpack_conv_wgrad": "ppiiiip",
+    "cris_pack_conv_weight_scaled": "pppiiiip",
+    "cris_pack_matrix_scaled": "pppqiip",
     "cris_pack_matrix": "ppqiip",
     "cris_batch_reduce": "piqpqiiiip",
     "cris_small_matmul": "pppiiiiip",

@@ -79,7 +79,8 @@ enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_RESID = 2, EPI_ACCUM = 3 };
 // runtime option bits, evaluated on the HOST and kept in one ordinary register: testing kernel-parameter fields
 // inside the chunk loop costs a constant-bank load -> uniform predicate -> branch chain (~50-100 cycles each with
 // only two warps per scheduler to hide it; ncu: stall_short_sb on UISETP after LDCU)
-enum { F_BIAS = 1, F_RELU = 2, F_FAST = 4, F_TMA = 8, F_DFP32 = 16, F_STATS = 32, F_WGRAD = 64, F_ALPHA = 128 };
+enum { F_BIAS = 1, F_RELU = 2, F_FAST = 4, F_TMA = 8, F_DFP32 = 16, F_STATS = 32, F_WGRAD = 64, F_ALPHA = 128,
+       F_RELU_POST = 256 /* ReLU after the residual add: relu(acc + bias + resid), folded eval-mode BatchNorm */ };
 
 struct ChunkCtx {
   long long drow, rrow;  // element offsets of this lane's row in D / resid (batch offsets included)
@@ -143,6 +144,10 @@ __device__ __forceinline__ void chunk_generic(const GemmKArgs& p, float (&v)[32]
         if (ncol0 + j < p.N) v[j] += bf2f(rp[j]);
     }
   }
+  if (p.act == CRIS_ACT_RELU_POST) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
   if (!cx.row_valid) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -199,6 +204,10 @@ __device__ __forceinline__ void chunk_fast(const GemmKArgs& p, float (&v)[32], c
         v[8 * j + 4] += e2.x; v[8 * j + 5] += e2.y; v[8 * j + 6] += e3.x; v[8 * j + 7] += e3.y;
       }
     }
+  }
+  if (flags & F_RELU_POST) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (!cx.row_valid) {
 #pragma unroll
@@ -770,9 +779,10 @@ static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream
     const bool b_al = a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
     const bool epi_match = ((EPI == EPI_ACCUM) ? (a->d_fp32 && a->accumulate) : !a->accumulate) &&
                            ((EPI == EPI_STATS) == (a->colstats != nullptr)) && ((EPI == EPI_RESID) == (a->resid != nullptr));
-    const bool fast = d_al && r_al && b_al && epi_match && (a->act == CRIS_ACT_NONE || a->act == CRIS_ACT_RELU) &&
+    const bool fast = d_al && r_al && b_al && epi_match && (a->act == CRIS_ACT_NONE || a->act == CRIS_ACT_RELU || a->act == CRIS_ACT_RELU_POST) &&
                       (EPI == EPI_ACCUM || a->d_col_stride <= 1);
-    kk.flags = (a->bias ? F_BIAS : 0) | (a->act == CRIS_ACT_RELU ? F_RELU : 0) | (fast ? F_FAST : 0) |
+    kk.flags = (a->bias ? F_BIAS : 0) | (a->act == CRIS_ACT_RELU ? F_RELU : 0) |
+               (a->act == CRIS_ACT_RELU_POST ? F_RELU_POST : 0) | (fast ? F_FAST : 0) |
                (kk.tma_store ? F_TMA : 0) | (a->d_fp32 ? F_DFP32 : 0) | (a->colstats ? F_STATS : 0) |
                (a->tap_mode == CRIS_TAP_WGRAD ? F_WGRAD : 0) | (a->alpha != 1.0f ? F_ALPHA : 0);
   }

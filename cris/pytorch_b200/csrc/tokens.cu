@@ -227,14 +227,15 @@ __global__ void ew_kernel(const EwArgs p) {
 
 // ---- weight packing: fp32 OIHW [Cout][Cin][taps] -> bf16 [Cout][taps][cin_pad] (zero padded) ----------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                        int Cin, int taps, int cin_pad) {
+                                        int Cin, int taps, int cin_pad, const float* __restrict__ row_scale = nullptr) {
   const long long total = (long long)Cout * taps * cin_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
     const int t = (int)((i / cin_pad) % taps);
     const int co = (int)(i / ((long long)cin_pad * taps));
-    out[i] = f2bf(ci < Cin ? w[((long long)co * Cin + ci) * taps + t] : 0.f);
+    const float sc = row_scale != nullptr ? row_scale[co] : 1.f;
+    out[i] = f2bf(ci < Cin ? w[((long long)co * Cin + ci) * taps + t] * sc : 0.f);
   }
 }
 // weight gradient of a k x k conv from the wgrad GEMM's tap-blocked layout back to the reference's OIHW:
@@ -266,13 +267,13 @@ __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, __nv_
 }
 // fp32 [rows][cols] -> bf16 [rows][ld] (zero padded), optional per-row scale
 __global__ void pack_matrix_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long rows,
-                                   int cols, int ld) {
+                                   int cols, int ld, const float* __restrict__ row_scale = nullptr) {
   const long long total = rows * ld;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % ld);
     const long long r = i / ld;
-    out[i] = f2bf(c < cols ? w[r * cols + c] : 0.f);
+    out[i] = f2bf(c < cols ? w[r * cols + c] * (row_scale != nullptr ? row_scale[r] : 1.f) : 0.f);
   }
 }
 // out[t, c] (+)= sum_b in[b*T + t, c]   (batch reduction of token gradients -> shared positional term)
@@ -400,6 +401,21 @@ int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void*
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream) {
   pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
                                                                                              taps, cin_pad);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_conv_weight_scaled(const float* w, const float* row_scale, void* out, int Cout, int Cin, int taps,
+                                 int cin_pad, void* stream) {
+  CRIS_CHECK_ARG(w && row_scale && out, "pack_conv_weight_scaled: null argument");
+  pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
+                                                                                             taps, cin_pad, row_scale);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_matrix_scaled(const float* w, const float* row_scale, void* out, int64_t rows, int cols, int ld,
+                            void* stream) {
+  CRIS_CHECK_ARG(w && row_scale && out, "pack_matrix_scaled: null argument");
+  pack_matrix_kernel<<<grid_for(rows * ld, 256), 256, 0, STREAM>>>(w, BF(out), rows, cols, ld, row_scale);
   CRIS_LAUNCH_OK();
   return 0;
 }

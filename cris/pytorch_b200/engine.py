@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import GemmArgs, call, gemm
 
-ACT_NONE, ACT_RELU, ACT_QGELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_QGELU, ACT_RELU_POST = 0, 1, 2, 3
 TAP_NONE, TAP_ACCUM, TAP_WGRAD = 0, 1, 2
 BN_EPS, LN_EPS, BN_MOMENTUM = 1e-5, 1e-5, 0.1
 PEER_SLOT_FLOATS, PEER_MAX_SLOTS = 4096, 1024  # CRIS_PEER_* in include/cris_b200.h
@@ -101,6 +101,27 @@ class PackedWeights:
         self.cache[name] = (key, m)
         return m
 
+    def get_folded(self, name: str, p: torch.Tensor, scale_ptr: int, as_matrix: bool = False) -> Mat:
+        """Eval mode: the same layouts with output channel co scaled by scale[co] (BatchNorm folded into the
+        convolution).  Re-packed on every call: the scale depends on the running statistics, not on p._version."""
+        ent = self.cache.get(name + "#folded")
+        w = p.detach()
+        if w.dim() == 4 and w.shape[2] == 3 and not as_matrix:
+            cout, cin = w.shape[0], w.shape[1]
+            cp = _r8(cin)
+            buf = ent.buf if ent is not None else torch.empty(cout, 9 * cp, dtype=torch.bfloat16, device=w.device)
+            call("cris_pack_conv_weight_scaled", w.data_ptr(), scale_ptr, buf.data_ptr(), cout, cin, 9, cp)
+            m = Mat(buf, cout, 9 * cp)
+        else:
+            rows = w.shape[0]
+            cols = w.numel() // rows
+            ld = _r8(cols)
+            buf = ent.buf if ent is not None else torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+            call("cris_pack_matrix_scaled", w.data_ptr(), scale_ptr, buf.data_ptr(), rows, cols, ld)
+            m = Mat(buf, rows, cols, ld)
+        self.cache[name + "#folded"] = m
+        return m
+
 
 def _bicubic_matrix(src: int, H: int, W: int) -> torch.Tensor:
     """[H*W, src*src] interpolation matrix of F.interpolate(mode='bicubic', align_corners=False) from a
@@ -161,6 +182,9 @@ class Engine:
         self.use_graphs = os.environ.get("CRIS_B200_GRAPHS", "1") != "0"
         self.gemm_log: Optional[list] = None  # profiling: (M,N,K,batch,...) of every GEMM launch, in order
         self.force_sync_bn = False  # tests: exercise the cross-rank BN exchange without SyncBatchNorm modules
+        # eval mode: BatchNorm folded into the producing convolution (weights x scale, shift as bias, residual + ReLU in
+        # the GEMM epilogue) instead of a bn_coeffs + bn_apply pass per layer
+        self.fold_eval_bn = os.environ.get("CRIS_B200_FOLD_EVAL_BN", "1") != "0"
         self.graphs: Dict[tuple, "GraphedStep"] = {}
         self.eval_graphs: Dict[tuple, "GraphedEval"] = {}
         self._counter: Optional[torch.Tensor] = None
@@ -821,8 +845,35 @@ class Run:
         return z, part, n_tiles
 
     def conv_bn(self, x: Mat, conv_name: str, bn_prefix: str, k: int, relu=True, resid=None, out=None, cin=None):
+        if not self.training and self.e.fold_eval_bn:
+            return self.conv_bn_folded(x, conv_name, bn_prefix, k, relu, resid, out, cin)
         z, part, nt = self.conv(x, conv_name, k, stats=self.training, cin=cin)
         return self.bn_forward(z, bn_prefix, relu, resid, out, part, nt)
+
+    def conv_bn_folded(self, x: Mat, conv_name: str, bn_prefix: str, k: int, relu, resid, out, cin) -> Mat:
+        """model.eval(): y = relu?(conv(x) * scale + shift (+ resid)) with scale = gamma / sqrt(running_var + eps),
+        shift = beta - running_mean * scale — the scale is folded into the bf16 weights, the shift is the GEMM's
+        bias, residual add and ReLU run in the GEMM epilogue: no BatchNorm pass over the activations at all
+        (model/layers.py:8-11, model/clip.py:44-57 under model.eval(); engine/engine.py:100,171)."""
+        Wt = self.P[conv_name]
+        cout, w_cols = Wt.shape[0], Wt.shape[1]
+        cin = w_cols if cin is None else cin
+        cin_pad = _r8(w_cols)
+        gamma, beta = self.P[bn_prefix + ".weight"], self.P[bn_prefix + ".bias"]
+        rm, rv = self.Bf[bn_prefix + ".running_mean"], self.Bf[bn_prefix + ".running_var"]
+        coef = self.f32(4 * cout)  # scale | shift | mean | invstd
+        call("cris_bn_coeffs", None, 1.0, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(),
+             rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * cout, coef.data_ptr() + 8 * cout,
+             coef.data_ptr() + 12 * cout, cout, 0)
+        wp = self.e.packed.get_folded(conv_name, Wt, coef.data_ptr())
+        y = out if out is not None else self.new(x.rows, cout, False, x.geom)
+        act = ACT_NONE if not relu else (ACT_RELU_POST if resid is not None else ACT_RELU)
+        self.gemm(x, wp, y, x.rows, cout, cin, bias=coef.data_ptr() + 4 * cout, act=act, resid=resid,
+                  mask_geom=x.geom, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE, taps=9 if k == 3 else 1,
+                  tap_off=self.taps_of(x.geom) if k == 3 else None, b_tap_k=cin_pad if k == 3 else 0)
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(coef)  # the bias vector must outlive the launch (eager mode frees on scope exit otherwise)
+        return y
 
     # ---- resampling -------------------------------------------------------------------------------
     def avgpool(self, x: Mat, out: Optional[Mat] = None) -> Mat:

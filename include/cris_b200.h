@@ -37,7 +37,9 @@ uint64_t cris_launch_count(void);           /* kernels launched by this library 
 void cris_add_launch_count(uint64_t n);     /* a replayed CUDA graph adds the launches it contains */
 
 /* ---- the GEMM / implicit-GEMM-conv core --------------------------------------------- */
-enum { CRIS_ACT_NONE = 0, CRIS_ACT_RELU = 1, CRIS_ACT_QUICKGELU = 2 };
+/* RELU / QUICKGELU act on (acc*alpha + bias) before the residual is added; RELU_POST after it:
+ * relu(acc + bias + resid) = eval-mode conv + BatchNorm (folded) + identity + ReLU (model/clip.py:44-57) */
+enum { CRIS_ACT_NONE = 0, CRIS_ACT_RELU = 1, CRIS_ACT_QUICKGELU = 2, CRIS_ACT_RELU_POST = 3 };
 enum { CRIS_TAP_NONE = 0, CRIS_TAP_ACCUM = 1, CRIS_TAP_WGRAD = 2 };
 
 /*
@@ -206,6 +208,12 @@ int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps
  * the reference's OIHW gradient gw[co][ci][t] (autograd of nn.Conv2d, model/clip.py:17-25) */
 int cris_unpack_conv_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int cin_pad, void* stream);
 int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
+/* the same bf16 kernel layouts with every output row (= output channel) multiplied by row_scale[row] first:
+ * eval-mode BatchNorm folded into the convolution, w'[co] = w[co] * gamma[co]/sqrt(running_var[co]+eps)
+ * (model/layers.py:8-11, model/clip.py:17-25 in model.eval()) */
+int cris_pack_conv_weight_scaled(const float* w, const float* row_scale, void* out, int Cout, int Cin, int taps, int cin_pad,
+                                 void* stream);
+int cris_pack_matrix_scaled(const float* w, const float* row_scale, void* out, int64_t rows, int cols, int ld, void* stream);
 int cris_batch_reduce(const void* in, int in_fp32, int64_t ldin, float* out, int64_t ldo, int B, int T, int C,
                       int accumulate, void* stream);
 int cris_small_matmul(const float* R, const float* X, float* out, int M, int K, int C, int transpose_r, int accumulate,

@@ -11,13 +11,13 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SETTINGS = [
     ("baseline", {}),
-    ("CRIS_B200_FASTDIV=1", {"CRIS_B200_FASTDIV": "1"}),
+    ("CRIS_B200_BN_STREAM=0 (register-streaming BatchNorm kernels)", {"CRIS_B200_BN_STREAM": "0"}),
     ("CRIS_B200_BIAS_MMA=1", {"CRIS_B200_BIAS_MMA": "1"}),
-    ("CRIS_B200_FASTDIV=1 CRIS_B200_BIAS_MMA=1", {"CRIS_B200_FASTDIV": "1", "CRIS_B200_BIAS_MMA": "1"}),
-    ("CRIS_B200_BWD_SEGMENTS=3", {"CRIS_B200_BWD_SEGMENTS": "3"}),
-    ("CRIS_B200_HALO_CONV=1 (unverified kernel)", {"CRIS_B200_HALO_CONV": "1"}),
-    ("CRIS_B200_TORCH_ADAM=1", {"CRIS_B200_TORCH_ADAM": "1"}),
+    ("CRIS_B200_HALO_CONV=1", {"CRIS_B200_HALO_CONV": "1"}),
+    ("CRIS_B200_HALO_CONV=1 CRIS_B200_BIAS_MMA=1", {"CRIS_B200_HALO_CONV": "1", "CRIS_B200_BIAS_MMA": "1"}),
 ]
+if os.environ.get("CRIS_SWEEP"):  # comma-separated subset / custom settings: NAME=VAL+NAME=VAL,...
+    SETTINGS = [("baseline", {})] + [(x, dict(kv.split("=") for kv in x.split("+"))) for x in os.environ["CRIS_SWEEP"].split(",")]
 
 
 def main():

@@ -18,6 +18,17 @@ for part in $PARTS; do
       CRIS_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_parity_gpu.py -q --no-header -p no:cacheprovider -rA \
         > gpurun_out/${TAG}_tests_ops.log 2>&1
       echo "[tests_ops] rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_tests_ops.log | tail -30 ;;
+    bnbench)
+      timeout 300 python tools/bn_bench.py --stream 1 > gpurun_out/${TAG}_bnbench.log 2>&1
+      timeout 300 python tools/bn_bench.py --stream 0 >> gpurun_out/${TAG}_bnbench.log 2>&1
+      echo "[bnbench] rc=$?"; cat gpurun_out/${TAG}_bnbench.log ;;
+    ncu_bn)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:bn_stream -s 40 -c 12 -f \
+        -o gpurun_out/${TAG}_bn_stream python tools/bn_bench.py --stream 1 > gpurun_out/${TAG}_ncu_bn.log 2>&1
+      echo "[ncu_bn] rc=$?" ;;
+    sweep)
+      timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
+      echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
     tests_new)
       timeout 1200 python -m pytest tests/test_parity_full_gpu.py tests/test_syncbn_equiv_gpu.py tests/test_dropin_gpu.py -q --no-header \
         -p no:cacheprovider -rA -s > gpurun_out/${TAG}_tests_new.log 2>&1
