@@ -23,8 +23,8 @@ for part in $PARTS; do
       timeout 300 python tools/bn_bench.py --stream 0 >> gpurun_out/${TAG}_bnbench.log 2>&1
       echo "[bnbench] rc=$?"; cat gpurun_out/${TAG}_bnbench.log ;;
     ncu_bn)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:bn_stream -s 40 -c 12 -f \
-        -o gpurun_out/${TAG}_bn_stream python tools/bn_bench.py --stream 1 > gpurun_out/${TAG}_ncu_bn.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:bn_stream -c 6 -f \
+        -o gpurun_out/${TAG}_bn_stream python tools/bn_bench.py --stream 1 --once > gpurun_out/${TAG}_ncu_bn.log 2>&1
       echo "[ncu_bn] rc=$?" ;;
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
