@@ -110,6 +110,12 @@ def lib():
         L.cris_peer_buffer_close.argtypes = [C.c_void_p, C.c_int]
         L.cris_peer_allreduce_f32.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_int, C.c_double, C.c_void_p]
+        L.cris_peer_bn_sync_fwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                            C.c_void_p]
+        L.cris_peer_bn_sync_bwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         for name, sig in _SIGS.items():
             fn = getattr(L, name)
             fn.argtypes = [_T[ch] for ch in sig]
@@ -126,7 +132,7 @@ def exported_symbols():
     return ["cris_last_error", "cris_abi_version", "cris_device_check",
             "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_plan", "cris_gemm_args_size", "cris_gemm_args_last_offset",
             "cris_peer_buffer_bytes", "cris_peer_buffer_create", "cris_peer_buffer_open", "cris_peer_buffer_close",
-            "cris_peer_allreduce_f32", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]
+            "cris_peer_allreduce_f32", "cris_peer_bn_sync_fwd", "cris_peer_bn_sync_bwd", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

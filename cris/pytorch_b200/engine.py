@@ -695,6 +695,10 @@ class Run:
                                    f"(exchange site {self.xslot}, {t.numel()} floats)")
             dist.all_reduce(t)
 
+    def fused_sync_ok(self, C: int) -> bool:
+        return (self.xchg is not None and 2 * C <= PEER_SLOT_FLOATS
+                and os.environ.get("CRIS_B200_FUSED_SYNCBN", "1") != "0")
+
     def bn_forward(self, z: Mat, prefix: str, relu: bool, resid: Optional[Mat] = None, out: Optional[Mat] = None,
                    partials=None, n_tiles=0) -> Mat:
         """BatchNorm over the rows of z (+ residual, ReLU).  Training = batch statistics (SyncBN-equivalent
@@ -715,7 +719,12 @@ class Run:
                 call("cris_col_reduce", 0, z.ptr, z.ld, 0, None, 0, None, 0, None, 0, 0, None, None, None, None, z.rows,
                      C, 0, z.hp, z.wp, partials.data_ptr(), nb)
             sums = self.f32(2 * C)
-            if self.sync_bn:
+            if self.sync_bn and self.fused_sync_ok(C):
+                # ONE kernel per exchange site: partials -> local sums -> pushed to every peer over NVLink ->
+                # rank-ordered global sums -> coefficients + running statistics (csrc/peer.cu peer_bn_sync_kernel)
+                self.xchg.bn_sync_fwd(self.xslot, partials, n_tiles, C, count, gamma, beta, BN_EPS, BN_MOMENTUM, rm, rv, coef)
+                self.xslot += 1
+            elif self.sync_bn:
                 call("cris_bn_reduce_partials", partials.data_ptr(), n_tiles, C, sums.data_ptr())
                 self.allreduce(sums)
                 call("cris_bn_coeffs", sums.data_ptr(), count, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM,
@@ -750,9 +759,13 @@ class Run:
             bs = self.f32(2 * C)
             # parameter gradients are LOCAL sums (DDP averages them), dx needs the GLOBAL sums
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
-            call("cris_stats_finalize_bwd", part.data_ptr(), min(nb, 64), C, bs.data_ptr(), gb.data_ptr(), gg.data_ptr())
-            if self.sync_bn:
-                self.allreduce(bs)
+            if self.sync_bn and self.fused_sync_ok(C):
+                self.xchg.bn_sync_bwd(self.xslot, part, min(nb, 64), C, bs, gb, gg)
+                self.xslot += 1
+            else:
+                call("cris_stats_finalize_bwd", part.data_ptr(), min(nb, 64), C, bs.data_ptr(), gb.data_ptr(), gg.data_ptr())
+                if self.sync_bn:
+                    self.allreduce(bs)
             dz = self.new(z.rows, C, False, z.geom)
             dres_ptr, dres_ld, dres_acc = None, 0, 0
             if resid is not None and resid.need_grad:

@@ -71,6 +71,23 @@ class PeerExchange:
         if rc != 0:
             raise RuntimeError(f"libcris_b200 cris_peer_allreduce_f32 failed: {_lib.lib().cris_last_error().decode()}")
 
+    def bn_sync_fwd(self, site, partials, n_tiles, C, count, gamma, beta, eps, momentum, rm, rv, coef):
+        """One fused exchange site (csrc/peer.cu peer_bn_sync_kernel): coef = [scale | shift | mean | invstd] (4C)."""
+        p0 = coef.data_ptr()
+        rc = _lib.lib().cris_peer_bn_sync_fwd(self.ptrs, self.world, self.rank, site, partials.data_ptr(), n_tiles, C,
+                                              float(count), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+                                              rm.data_ptr(), rv.data_ptr(), p0, p0 + 4 * C, p0 + 8 * C, p0 + 12 * C,
+                                              self.timeout_s, _lib.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"libcris_b200 cris_peer_bn_sync_fwd failed: {_lib.lib().cris_last_error().decode()}")
+
+    def bn_sync_bwd(self, site, partials, n_tiles, C, sums_out, grad_beta, grad_gamma):
+        rc = _lib.lib().cris_peer_bn_sync_bwd(self.ptrs, self.world, self.rank, site, partials.data_ptr(), n_tiles, C,
+                                              sums_out.data_ptr(), grad_beta.data_ptr(), grad_gamma.data_ptr(),
+                                              self.timeout_s, _lib.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"libcris_b200 cris_peer_bn_sync_bwd failed: {_lib.lib().cris_last_error().decode()}")
+
     def close(self):
         L = _lib.lib()
         for r in range(self.world):

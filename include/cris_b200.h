@@ -245,6 +245,19 @@ int cris_peer_buffer_close(void* dev_ptr, int owned);
  * timeout_s <= 0 -> 120 s; a peer that never arrives makes the kernel print and trap instead of hanging. */
 int cris_peer_allreduce_f32(void* const* peer_ptrs, int world, int rank, int slot, const float* in, float* out, int n,
                             double timeout_s, void* stream);
+/* One SyncBatchNorm exchange site in ONE kernel: local partials [n_tiles][2][C] -> this rank's (sum, sumsq) ->
+ * pushed into every peer's memory over NVLink -> rank-ordered global sums ->
+ *   fwd: scale/shift/mean/invstd + running-statistics update from the GLOBAL statistics (global_count = elements per
+ *        channel over all ranks) — torch.nn.SyncBatchNorm.forward (train.py:97-98)
+ *   bwd: grad_beta / grad_gamma = LOCAL (sum dz, sum dz*xhat) (DDP averages them), sums_out[2C] = GLOBAL sums for
+ *        cris_bn_bwd_apply — SyncBatchNorm.backward's all-reduce.
+ * `site` is the exchange-site index of the pass (every rank issues the same sequence); 2*C <= CRIS_PEER_SLOT_FLOATS. */
+int cris_peer_bn_sync_fwd(void* const* peer_ptrs, int world, int rank, int site, const float* partials, int n_tiles, int C,
+                          double global_count, const float* gamma, const float* beta, float eps, float momentum,
+                          float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                          double timeout_s, void* stream);
+int cris_peer_bn_sync_bwd(void* const* peer_ptrs, int world, int rank, int site, const float* partials, int n_tiles, int C,
+                          float* sums_out, float* grad_beta, float* grad_gamma, double timeout_s, void* stream);
 
 /* ---- optimizer step (SURVEY 8f "next" row: torch.optim.Adam driven by GradScaler, train.py:105-111,
  *      engine/engine.py:52-57).  One launch updates every tensor of a parameter group:

@@ -60,6 +60,37 @@ def _worker(rank, world, port, q):
             torch.cuda.synchronize(dev)
             for (slot, n), o in zip(sites[:3], outs):
                 bad += int(not torch.equal(o.cpu(), _expected(world, it, slot, n)))
+        # fused SyncBatchNorm sites (peer_bn_sync_kernel): partials -> push exchange -> coefficients, eagerly and from a
+        # graph, more sites than the ring has slots; reference = the same arithmetic in torch on the rank-ordered sums
+        for it in range(40):
+            C = (8, 64, 256, 2048)[it % 4]
+            nt = (1, 5, 64)[it % 3]
+            parts = [torch.randn(nt, 2, C, generator=torch.Generator().manual_seed(7000 + 10 * it + r)) for r in range(world)]
+            for p_ in parts:
+                p_[:, 1].abs_()
+                p_[:, 1] += 50.0 * nt  # keep the variance positive
+            gam, bet = torch.rand(C) + 0.5, torch.randn(C)
+            rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+            coef = torch.zeros(4 * C, device=dev)
+            count = 100.0 * world
+            ex.bn_sync_fwd(it, parts[rank].to(dev).contiguous(), nt, C, count, gam.to(dev), bet.to(dev), 1e-5, 0.1, rm, rv, coef)
+            tot = torch.zeros(2, C)
+            for r in range(world):
+                tot = tot + parts[r].sum(0)
+            mean = (tot[0].double() / count)
+            var = (tot[1].double() / count - mean * mean).clamp_min(0)
+            inv = torch.rsqrt(var.float() + 1e-5)
+            exp = torch.cat([gam * inv, bet - mean.float() * gam * inv, mean.float(), inv])
+            got = coef.cpu()
+            bad += int(not torch.allclose(got, exp, rtol=2e-4, atol=1e-5))
+            bad += int(not torch.allclose(rm.cpu(), 0.1 * mean.float(), rtol=2e-4, atol=1e-6))
+            # backward flavour: local sums -> parameter gradients, global sums out
+            bs, g0, g1 = torch.zeros(2 * C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            ex.bn_sync_bwd(1000 + it, parts[rank].to(dev).contiguous(), nt, C, bs, g0, g1)
+            loc = parts[rank].sum(0)
+            bad += int(not torch.allclose(g0.cpu(), loc[0], rtol=1e-4, atol=1e-4))
+            bad += int(not torch.allclose(g1.cpu(), loc[1], rtol=1e-4, atol=1e-4))
+            bad += int(not torch.allclose(bs.cpu(), tot.reshape(-1), rtol=1e-4, atol=1e-4))
         dist.barrier()
         ex.close()
         q.put((rank, "ok", bad))
