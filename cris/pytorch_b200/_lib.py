@@ -82,6 +82,8 @@ _SIGS = {
     "cris_dynconv_bce_fwd": "pqpqpiipppiiiip",
     "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
     "cris_adam_step": "piqddddddppp",
+    "cris_attention_fwd": "pqpqpqpqpiiiiffupp",
+    "cris_attention_bwd": "pqpqpqpqpq" "pppqpqpq" "iiii" "ffu" "pp",
     "cris_conv3x3_halo": "pqpqipqpiiiiip",
     "cris_pack_conv_weight_dgrad": "ppiiip",
 }

@@ -801,9 +801,10 @@ class Run:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         if (k == 3 and bias is None and cin in (32, 64) and cout in (32, 64) and x.geom is not None and not as_matrix
-                and os.environ.get("CRIS_B200_HALO_CONV", "0") == "1"):
-            # experimental small-channel path (csrc/conv_halo.cu): one halo tile per 128*SUB output rows, the nine
-            # taps are descriptor offsets into it instead of nine L2 re-reads
+                and os.environ.get("CRIS_B200_HALO_CONV", "1") == "1"):
+            # small-channel path (csrc/conv_halo.cu): one halo tile per 128*SUB output rows, the nine taps are
+            # descriptor offsets into it instead of nine L2 re-reads (measured: -1.1 ms per step, profiles/r02_flag_sweep.txt;
+            # CRIS_B200_HALO_CONV=0 selects the generic implicit GEMM)
             N_, H_, W_ = x.geom
             call("cris_conv3x3_halo", x.ptr, x.ld, wp.ptr, wp.ld, cin_pad, z.ptr, z.ld,
                  part.data_ptr() if stats else None, N_, H_, W_, cin, cout)
@@ -839,8 +840,8 @@ class Run:
                 slot, acc = self.grad_slot(x)
                 n_in = min(cin, x.C)
                 if (k == 3 and not acc and n_in == cin and cin in (32, 64) and cout in (32, 64) and x.geom is not None
-                        and not as_matrix and os.environ.get("CRIS_B200_HALO_CONV", "0") == "1"):
-                    # experimental: dx = conv3x3(dz, mirrored / transposed weights) through the halo-tile kernel
+                        and not as_matrix and os.environ.get("CRIS_B200_HALO_CONV", "1") == "1"):
+                    # dx = conv3x3(dz, mirrored / transposed weights) through the halo-tile kernel
                     cop = _r8(cout)
                     wt = self.new(cin, 9 * cop)
                     call("cris_pack_conv_weight_dgrad", self.P[wname].data_ptr(), wt.ptr, cout, cin, cop)
@@ -960,7 +961,7 @@ class Run:
                 self.ew(0, Mat(dy.buf, dy.rows, wpad, dy.ld, True, ptr=dy.ptr), None, Mat(t.buf, t.rows, wpad, wpad))
                 dy = t
             if bname:
-                if os.environ.get("CRIS_B200_BIAS_MMA", "0") == "1" and dy.rows >= 1024 and n_out % 8 == 0:
+                if os.environ.get("CRIS_B200_BIAS_MMA", "1") == "1" and dy.rows >= 1024 and n_out % 8 == 0:
                     # bias gradient on the tensor cores: 1^T . dy as an M = 1 GEMM (the ones vector is the only
                     # in-bounds row of the A box, TMA zero-fills the other 127); split-K atomics land directly in
                     # the zero-filled gradient buffer: one launch instead of reduce + finalize + two copies
@@ -1063,6 +1064,8 @@ class Run:
         model/clip.py:119-139,255-260 and model/layers.py:235,240-243).  q,k,v: [B*L, heads*64] bf16 (possibly
         column slices of a packed projection)."""
         E = heads * 64
+        if (Lk >= 64 and not causal and not key_pad and os.environ.get("CRIS_B200_FUSED_ATTN", "1") != "0"):
+            return self.attention_fused(q, k, v, B, heads, Lq, Lk, p_drop)
         Lkp = _r8(Lk)
         nb = B * heads
         S = self.new(nb * Lq, Lk, False, None, ld=Lkp)
@@ -1102,6 +1105,35 @@ class Run:
             self.gemm(dP, q, slot, Lk, 64, Lq, a_mn=1, b_mn=1, batch=nb, batch_inner=heads, sA=sS,
                       sB=(Lq * q.ld, 64), sD=(Lk * slot.ld, 64), alpha=alpha, resid=slot if acc else None,
                       sR=(Lk * slot.ld, 64), a_rows=Lq, b_rows=Lq)
+
+        if self.training:
+            self.on_backward(bwd)
+        return o
+
+    def attention_fused(self, q: Mat, k: Mat, v: Mat, B, heads, Lq, Lk, p_drop=0.0) -> Mat:
+        """The same attention with the scores kept on the SM (csrc/attention.cu): one forward kernel, and a backward
+        that recomputes P from Q, K and the saved row log-sum-exp — S, P, dropout(P), dP never exist in HBM."""
+        E = heads * 64
+        o = self.new(B * Lq, E)
+        lse = self.f32(B * heads * Lq)
+        sd = self.seed() if p_drop > 0 else 0
+        alpha = 1.0 / 8.0
+        call("cris_attention_fwd", q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, o.ptr, o.ld, lse.data_ptr(), B, heads, Lq, Lk,
+             alpha, float(p_drop), int(sd), self.seed_dev if p_drop > 0 else None)
+
+        def bwd():
+            do = self.grad_of(o)
+            if do is None:
+                return
+            dq_acc = Mat(self.zeros_f32(B * Lq * E), B * Lq, E, fp32=True)
+            dk, dv = self.new(B * Lk, E), self.new(B * Lk, E)
+            dsum = self.f32(B * heads * Lq)
+            call("cris_attention_bwd", q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, o.ptr, o.ld, do.ptr, do.ld, lse.data_ptr(),
+                 dsum.data_ptr(), dq_acc.ptr, dq_acc.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, B, heads, Lq, Lk, alpha,
+                 float(p_drop), int(sd), self.seed_dev if p_drop > 0 else None)
+            for src, owner in ((dq_acc, q), (dk, k), (dv, v)):
+                slot, acc = self.grad_slot(owner)
+                self.ew(0, src, slot if acc else None, slot)
 
         if self.training:
             self.on_backward(bwd)

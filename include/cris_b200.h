@@ -259,6 +259,24 @@ int cris_peer_bn_sync_fwd(void* const* peer_ptrs, int world, int rank, int site,
 int cris_peer_bn_sync_bwd(void* const* peer_ptrs, int world, int rank, int site, const float* partials, int n_tiles, int C,
                           float* sums_out, float* grad_beta, float* grad_gamma, double timeout_s, void* stream);
 
+/* ---- fused multi-head attention for 64-wide heads (csrc/attention.cu): O = dropout(softmax(alpha Q K^T)) V per
+ *      (image, head), scores kept in tensor memory / shared memory (never written to HBM) — the core of
+ *      F.multi_head_attention_forward as called at model/layers.py:233-237 (decoder self attention, 676 keys,
+ *      attention dropout) and model/clip.py:119-139 (AttentionPool2d).  q [B*Lq, heads*64], k / v [B*Lk, heads*64]
+ *      bf16 with their own pitches (column slices of packed projections); lse [B*heads*Lq] fp32 receives the row
+ *      log2-sum-exp for the backward.  No masks: causal / key-padded attention (17 keys) stays on the
+ *      cris_gemm + cris_softmax path.  Dropout masks are the same pure function of (seed + *seed_dev, element index
+ *      ((b*heads+h)*Lq + q)*round8(Lk) + k) that cris_softmax_fwd uses.
+ *      backward: d_scratch [B*heads*Lq] fp32 workspace; dq_acc fp32 [B*Lq, heads*64] must be ZEROED by the caller
+ *      (the key blocks of one image/head add into it); dk, dv bf16 [B*Lk, heads*64] are overwritten. */
+int cris_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                       float* lse, int B, int heads, int Lq, int Lk, float alpha, float p_drop, uint64_t seed,
+                       const uint64_t* seed_dev, void* stream);
+int cris_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                       int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* d_scratch, float* dq_acc,
+                       int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int heads, int Lq, int Lk,
+                       float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
+
 /* ---- optimizer step (SURVEY 8f "next" row: torch.optim.Adam driven by GradScaler, train.py:105-111,
  *      engine/engine.py:52-57).  One launch updates every tensor of a parameter group:
  *      g' = g / *grad_scale (+ weight_decay * p); m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).

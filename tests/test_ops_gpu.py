@@ -223,12 +223,10 @@ def test_conv_bn_train_magic_division_kernels(monkeypatch, k, cin, cout, resid, 
     test_conv_bn_train(k, cin, cout, resid, relu)
 
 
-@pytest.mark.skipif(os.environ.get("CRIS_B200_EXPERIMENTAL", "0") != "1",
-                    reason="experimental halo-tile convolution (csrc/conv_halo.cu): set CRIS_B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("N,H,W,cin,cout", [(2, 20, 18, 32, 32), (2, 20, 18, 32, 64), (3, 30, 30, 64, 64),
                                             (1, 6, 208, 32, 64), (2, 104, 104, 64, 64)])
 def test_conv_halo_matches_gemm(monkeypatch, N, H, W, cin, cout):
-    """CRIS_B200_HALO_CONV=1 routes 32/64-channel 3x3 convolutions through the halo-tile kernel; output and
+    """CRIS_B200_HALO_CONV=1 (the default) routes 32/64-channel 3x3 convolutions through the halo-tile kernel; output and
     BatchNorm column statistics must equal the default implicit-GEMM path (same bf16 products, fp32 accumulation
     in a different order: 1e-2 relative on z, 2e-2 on the statistics)."""
     g = torch.Generator().manual_seed(N * 1000 + W)
@@ -393,6 +391,47 @@ def test_attention(Lq, Lk, heads, causal, key_pad):
     assert rel(out_t(run.grad_of(vm)), vr.grad) < 2.5e-2
     assert rel(out_t(run.grad_of(qm)), qr.grad) < 3e-2
     assert rel(out_t(run.grad_of(km)), kr.grad) < 3e-2
+
+
+@pytest.mark.parametrize("Lq,Lk,heads,B,p_drop", [(676, 676, 8, 3, 0.1), (169, 169, 4, 2, 0.0), (300, 77, 2, 2, 0.25),
+                                                  (128, 128, 1, 1, 0.0), (129, 65, 2, 2, 0.1)])
+def test_fused_attention_matches_materialised_path(monkeypatch, Lq, Lk, heads, B, p_drop):
+    """csrc/attention.cu (scores in TMEM / shared memory) against the cris_gemm + cris_softmax path it replaces, with
+    the SAME dropout masks (both hash (seed, ((b*heads+h)*Lq+q)*round8(Lk)+k)), on column slices of a packed
+    projection (pitch 3E) with ragged tile edges; and against fp32 torch math when there is no dropout."""
+    from cris.pytorch_b200.engine import Mat
+    g = torch.Generator().manual_seed(Lq * 3 + Lk)
+    E = heads * 64
+    qkv = _bf(torch.randn(B * Lq, 3 * E, generator=g)).cuda().to(torch.bfloat16)
+    kv = _bf(torch.randn(B * Lk, 2 * E, generator=g)).cuda().to(torch.bfloat16)
+    go = _bf(torch.randn(B * Lq, E, generator=g))
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CRIS_B200_FUSED_ATTN", flag)
+        run = _mk_run({}, p_drop=p_drop)
+        run.seed_base, run.n_seed = 4242, 0
+        qroot = Mat(qkv, B * Lq, 3 * E)
+        kroot = Mat(kv, B * Lk, 2 * E)
+        qm, km, vm = qroot.cols(E, 2 * E), kroot.cols(0, E), kroot.cols(E, 2 * E)
+        o = run.attention(qm, km, vm, B, heads, Lq, Lk, p_drop=p_drop)
+        set_grad(run, o, go)
+        backward(run)
+        res[flag] = (out_t(o), out_t(run.grad_of(qm)), out_t(run.grad_of(km)), out_t(run.grad_of(vm)))
+    for a, b_, tol in zip(res["1"], res["0"], (1.2e-2, 2.5e-2, 2.5e-2, 2e-2)):
+        assert rel(a, b_) < tol
+    if p_drop == 0.0:
+        q = qkv[:, E:2 * E].float().cpu()
+        k, v = kv[:, :E].float().cpu(), kv[:, E:].float().cpu()
+        qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+        qh = qr.view(B, Lq, heads, 64).transpose(1, 2)
+        kh = kr.view(B, Lk, heads, 64).transpose(1, 2)
+        vh = vr.view(B, Lk, heads, 64).transpose(1, 2)
+        ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, -1) @ vh).transpose(1, 2).reshape(B * Lq, E)
+        ref.backward(go)
+        assert rel(res["1"][0], ref.detach()) < 1.2e-2
+        assert rel(res["1"][3], vr.grad) < 2e-2
+        assert rel(res["1"][1], qr.grad) < 2.5e-2
+        assert rel(res["1"][2], kr.grad) < 2.5e-2
 
 
 def test_avgpool_upsample():
