@@ -29,6 +29,13 @@ for part in $PARTS; do
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
+    tests_attn)
+      timeout 600 python -m pytest tests/test_ops_gpu.py -k "attention" -q --no-header -p no:cacheprovider -rA -x \
+        > gpurun_out/${TAG}_tests_attn.log 2>&1
+      echo "[tests_attn] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error|timeout|cris_b200" gpurun_out/${TAG}_tests_attn.log | tail -30 ;;
+    tests_peer)
+      timeout 600 python -m pytest tests/test_peer_gpu.py -q --no-header -p no:cacheprovider -rA > gpurun_out/${TAG}_tests_peer.log 2>&1
+      echo "[tests_peer] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error" gpurun_out/${TAG}_tests_peer.log | tail -10 ;;
     tests_new)
       timeout 1200 python -m pytest tests/test_parity_full_gpu.py tests/test_syncbn_equiv_gpu.py tests/test_dropin_gpu.py -q --no-header \
         -p no:cacheprovider -rA -s > gpurun_out/${TAG}_tests_new.log 2>&1
