@@ -233,14 +233,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     ptx::mbar_wait(o_full, 0, 890);
     ptx::tc_fence_after();
     const float inv = p.inv_keep / l;
-    if (q < p.Lq) {
-      if (p.lse != nullptr) p.lse[(size_t)(b * p.heads + h) * p.Lq + q] = mt + log2f(l);
-      __nv_bfloat16* op = p.O + ((long long)b * p.Lq + q) * p.ldo + h * 64;
+    const bool row_ok = q < p.Lq;
+    if (row_ok && p.lse != nullptr) p.lse[(size_t)(b * p.heads + h) * p.Lq + q] = mt + log2f(l);
+    __nv_bfloat16* op = p.O + ((long long)b * p.Lq + q) * p.ldo + h * 64;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), v);
-        ptx::tmem_ld_wait();
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, only valid rows store
+      ptx::tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), v);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           float o[8];
@@ -248,13 +250,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g8 * 8 + i]) * inv;
           st8(op + c * 32 + g8 * 8, o);
         }
-      }
-    } else {  // keep the warp-collective TMEM loads aligned across the warp
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), v);
-        ptx::tmem_ld_wait();
       }
     }
   }
@@ -447,6 +442,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       ptx::mbar_arrive(dq_empty);
     }
     // dK, dV of this key block (every MMA has completed: the last dq_full commit covers them)
+    ptx::tc_fence_after();
     const int key = k0 + r;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {

@@ -30,7 +30,7 @@ for part in $PARTS; do
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
     tests_attn)
-      timeout 600 python -m pytest tests/test_ops_gpu.py -k "attention" -q --no-header -p no:cacheprovider -rA -x \
+      timeout 150 python -m pytest tests/test_ops_gpu.py -k "attention" -q --no-header -p no:cacheprovider -rA -x \
         > gpurun_out/${TAG}_tests_attn.log 2>&1
       echo "[tests_attn] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error|timeout|cris_b200" gpurun_out/${TAG}_tests_attn.log | tail -30 ;;
     tests_peer)
