@@ -19,8 +19,10 @@
 //   dQ_i = dS K (TMEM -> fp32 vector atomics into the dQ accumulator, 6 key blocks add into one row).
 //   The P / dS tiles are written once as [query][key] and read by the tensor core both K-major (dQ) and MN-major
 //   (the transposed products dV, dK): no transposition pass.
-// Warp roles (192 threads): warps 0-3 softmax + epilogue (one TMEM lane = one row per thread), warp 4 TMA producer,
-// warp 5 TMEM allocator + single-thread MMA issuer.
+// Warp roles (320 threads): warps 0-7 softmax + epilogue — warp w owns TMEM lanes 32*(w%4).. (one row per thread)
+// and the column half w/4 of every 128-column block, so every scheduler has softmax work (the phase is
+// instruction-issue bound: exp2 + dropout hash + bf16 pack per score); warp 8 TMA producer; warp 9 TMEM allocator +
+// single-thread MMA issuer.
 #include <cudaTypedefs.h>
 
 #include <mutex>
@@ -30,7 +32,8 @@
 
 namespace cris {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;
+constexpr int AT_SM_THREADS = 256;  // softmax / epilogue threads (warps 0-7)
 constexpr int AT_TILE = 16384;  // 128 rows x 64 bf16 = one 128B-swizzled box
 
 struct AttnArgs {
@@ -50,6 +53,13 @@ struct AttnArgs {
   __nv_bfloat16* dK; long long lddk;
   __nv_bfloat16* dV; long long lddv;
 };
+
+__device__ __forceinline__ float fast_exp2(float x) {  // x <= 0 here; MUFU.EX2, ~2 ulp
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int k0, const float* v) {
   // 8 consecutive keys k0..k0+7 of row `row` into a [128 x 128] bf16 tile stored as two 128B-swizzled [128 x 64] halves
@@ -77,7 +87,8 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, int k16) {
 // forward
 // ================================================================================================================
 struct FwdSmem {
-  static constexpr int Q = 0, KV = AT_TILE, P = 4 * AT_TILE, BAR = 6 * AT_TILE, BYTES = 6 * AT_TILE + 256 + 1024;
+  static constexpr int Q = 0, KV = AT_TILE, P = 4 * AT_TILE, BAR = 6 * AT_TILE, XCH = 6 * AT_TILE + 256,
+                       BYTES = 6 * AT_TILE + 256 + 1024 /* row-statistics exchange [2][128] */ + 1024 /* align */;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -90,11 +101,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   uint64_t* kv_full = bars + 1;       // [3]
   uint64_t* kv_empty = bars + 4;      // [3]
   uint64_t* s_full = bars + 7;
-  uint64_t* s_empty = bars + 8;       // 128 arrivals
-  uint64_t* p_full = bars + 9;        // 128 arrivals
+  uint64_t* s_empty = bars + 8;       // 256 arrivals
+  uint64_t* p_full = bars + 9;        // 256 arrivals
   uint64_t* p_empty = bars + 10;
   uint64_t* o_full = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xch = reinterpret_cast<float*>(smem + FwdSmem::XCH);  // [2 column halves][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Lk + 127) / 128;
@@ -103,21 +115,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 3; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_empty, 128);
-    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(s_empty, AT_SM_THREADS);
+    ptx::mbar_init(p_full, AT_SM_THREADS);
     ptx::mbar_init(p_empty, 1);
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); }
-  if (warp == 5) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 8 && lane == 0) { ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); }
+  if (warp == 9) ptx::tmem_alloc<256>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(q_full, AT_TILE);
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         ptx::tma_load_4d(smem + FwdSmem::KV + s * AT_TILE, is_v ? &tmV : &tmK, &kv_full[s], 0, j * 128, h, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idS = ptx::make_idesc_bf16(128, 128, 0, 0);
@@ -170,9 +182,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       ptx::umma_commit(o_full);
     }
   } else {
-    // ------------------------------ softmax + epilogue (thread = query row) ------------------------------
-    const int r = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ------------------------------ softmax + epilogue ------------------------------
+    // thread = (query row r, column half ch): TMEM lanes 32*(warp%4).., columns ch*64.. of every 128-column block
+    const int quad = warp & 3, ch = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int q = q0 + r;
     uint64_t seed = p.seed;
     if (p.seed_dev != nullptr) seed += *p.seed_dev;
@@ -180,67 +194,73 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     uint8_t* sP = smem + FwdSmem::P;
     float m = -INFINITY;
     int ns = 0;
-    for (int j = 0; j < nkv; ++j, ++ns) {       // pass 1: row maximum
+    for (int j = 0; j < nkv; ++j, ++ns) {       // pass 1: row maximum (this thread's column half)
       ptx::mbar_wait(s_full, ((uint32_t)ns) & 1u, 860);
       ptx::tc_fence_after();
-      const int valid = p.Lk - j * 128;
+      const int valid = p.Lk - j * 128 - ch * 64;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tS + lane_off + (uint32_t)(c * 32), v);
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(ch * 64 + c * 16), v);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+        for (int i = 0; i < 16; ++i)
+          if (c * 16 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
     }
-    const float mt = m * p.scale_log2;  // alpha > 0: max commutes with the scaling
+    xch[ch * 128 + r] = m;
+    softmax_bar();
+    m = fmaxf(xch[r], xch[128 + r]);
+    softmax_bar();                              // both halves have read the maxima before xch is reused for the sums
+    const float mt = m * p.scale_log2;          // alpha > 0: max commutes with the scaling
     float l = 0.f;
     for (int j = 0; j < nkv; ++j, ++ns) {       // pass 2: probabilities -> P tile
       ptx::mbar_wait(s_full, ((uint32_t)ns) & 1u, 870);
       if (j > 0) ptx::mbar_wait(p_empty, ((uint32_t)(j - 1)) & 1u, 880);
       ptx::tc_fence_after();
-      const int valid = p.Lk - j * 128;
+      const int valid = p.Lk - j * 128 - ch * 64;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tS + lane_off + (uint32_t)(c * 32), v);
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(ch * 64 + c * 16), v);
         ptx::tmem_ld_wait();
-        float e[32];
+        float e[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mt));
-          e[i] = (c * 32 + i < valid) ? x : 0.f;
+        for (int i = 0; i < 16; ++i) {
+          const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mt));
+          e[i] = (c * 16 + i < valid) ? x : 0.f;
           l += e[i];
         }
         if (p.drop_thresh != 0u) {
-          const uint64_t base = row_idx + (uint64_t)(j * 128 + c * 32);
+          const uint64_t base = row_idx + (uint64_t)(j * 128 + ch * 64 + c * 16);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 16; ++i)
             if (!drop_keep(seed, base + (uint64_t)i, p.drop_thresh)) e[i] = 0.f;
         }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) st_tile_chunk(sP, r, c * 32 + g8 * 8, &e[g8 * 8]);
+        st_tile_chunk(sP, r, ch * 64 + c * 16, &e[0]);
+        st_tile_chunk(sP, r, ch * 64 + c * 16 + 8, &e[8]);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
       ptx::mbar_arrive(p_full);
     }
-    // epilogue
+    xch[ch * 128 + r] = l;
+    softmax_bar();
+    l = xch[r] + xch[128 + r];
+    // epilogue: this warp's 32 of the 64 output columns
     ptx::mbar_wait(o_full, 0, 890);
     ptx::tc_fence_after();
     const float inv = p.inv_keep / l;
     const bool row_ok = q < p.Lq;
-    if (row_ok && p.lse != nullptr) p.lse[(size_t)(b * p.heads + h) * p.Lq + q] = mt + log2f(l);
-    __nv_bfloat16* op = p.O + ((long long)b * p.Lq + q) * p.ldo + h * 64;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    if (row_ok && ch == 0 && p.lse != nullptr) p.lse[(size_t)(b * p.heads + h) * p.Lq + q] = mt + log2f(l);
+    __nv_bfloat16* op = p.O + ((long long)b * p.Lq + q) * p.ldo + h * 64 + ch * 32;
+    {
       uint32_t v[32];
       // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, only valid rows store
-      ptx::tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), v);
+      ptx::tmem_ld_32x32(tO + lane_off + (uint32_t)(ch * 32), v);
       ptx::tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -248,14 +268,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           float o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g8 * 8 + i]) * inv;
-          st8(op + c * 32 + g8 * 8, o);
+          st8(op + g8 * 8, o);
         }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<256>(tmem);
   }
@@ -296,11 +316,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   uint64_t* qd_full = bars + 1;       // [2]
   uint64_t* qd_empty = bars + 3;      // [2]
   uint64_t* sdp_full = bars + 5;
-  uint64_t* s_empty = bars + 6;       // 128
-  uint64_t* pds_full = bars + 7;      // 128
+  uint64_t* s_empty = bars + 6;       // 256
+  uint64_t* pds_full = bars + 7;      // 256
   uint64_t* pds_empty = bars + 8;
   uint64_t* dq_full = bars + 9;
-  uint64_t* dq_empty = bars + 10;     // 128
+  uint64_t* dq_empty = bars + 10;     // 256
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -310,24 +330,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&qd_full[s], 1); ptx::mbar_init(&qd_empty[s], 1); }
     ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(s_empty, 128);
-    ptx::mbar_init(pds_full, 128);
+    ptx::mbar_init(s_empty, AT_SM_THREADS);
+    ptx::mbar_init(pds_full, AT_SM_THREADS);
     ptx::mbar_init(pds_empty, 1);
     ptx::mbar_init(dq_full, 1);
-    ptx::mbar_init(dq_empty, 128);
+    ptx::mbar_init(dq_empty, AT_SM_THREADS);
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
   }
-  if (warp == 5) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
       ptx::tma_load_4d(smem + BwdSmem::K, &tmK, kv_full, 0, k0, h, b);
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         ptx::tma_load_4d(smem + BwdSmem::QD + s * 2 * AT_TILE + AT_TILE, &tmdO, &qd_full[s], 0, i * 128, h, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idS = ptx::make_idesc_bf16(128, 128, 0, 0);   // Q K^T, dO V^T
       constexpr uint32_t idT = ptx::make_idesc_bf16(128, 64, 1, 1);    // Pd^T dO, dS^T Q
@@ -377,63 +397,64 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       }
     }
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // thread = (query row r, column half ch) as in the forward; for the dK/dV epilogue r is the key row
+    const int quad = warp & 3, ch = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     uint64_t seed = p.seed;
     if (p.seed_dev != nullptr) seed += *p.seed_dev;
     uint8_t* sP = smem + BwdSmem::P;
     uint8_t* sDS = smem + BwdSmem::DS;
-    const int valid = p.Lk - k0;  // keys of this block that exist
+    const int valid = p.Lk - k0 - ch * 64;  // keys of this thread's column half that exist
     const size_t bh = (size_t)(b * p.heads + h);
     for (int i = 0; i < nq; ++i) {
       const int q = i * 128 + r;
       const bool row_ok = q < p.Lq;
       const float lse = row_ok ? p.lse[bh * p.Lq + q] : 0.f;
       const float Dq = row_ok ? p.Dsum[bh * p.Lq + q] : 0.f;
-      const uint64_t row_idx = (bh * (uint64_t)p.Lq + (uint64_t)q) * (uint64_t)p.LkPad + (uint64_t)k0;
+      const uint64_t row_idx = (bh * (uint64_t)p.Lq + (uint64_t)q) * (uint64_t)p.LkPad + (uint64_t)(k0 + ch * 64);
       ptx::mbar_wait(sdp_full, ((uint32_t)i) & 1u, 960);
       if (i > 0) ptx::mbar_wait(pds_empty, ((uint32_t)(i - 1)) & 1u, 970);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dv[32];
-        ptx::tmem_ld_32x32(tS + lane_off + (uint32_t)(c * 32), sv);
-        ptx::tmem_ld_32x32(tdP + lane_off + (uint32_t)(c * 32), dv);
+        uint32_t sv[16], dv[16];
+        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(ch * 64 + c * 16), sv);
+        ptx::tmem_ld_32x16(tdP + lane_off + (uint32_t)(ch * 64 + c * 16), dv);
         ptx::tmem_ld_wait();
-        float pd[32], ds[32];
+        float pd[16], ds[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (c * 32 + j < valid);
-          const float pr = ok ? exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse)) : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = row_ok && (c * 16 + j < valid);
+          const float pr = ok ? fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse)) : 0.f;
           bool keep = true;
-          if (p.drop_thresh != 0u) keep = drop_keep(seed, row_idx + (uint64_t)(c * 32 + j), p.drop_thresh);
+          if (p.drop_thresh != 0u) keep = drop_keep(seed, row_idx + (uint64_t)(c * 16 + j), p.drop_thresh);
           const float dpm = keep ? __uint_as_float(dv[j]) * p.inv_keep : 0.f;
           pd[j] = keep ? pr * p.inv_keep : 0.f;
           ds[j] = ok ? pr * (dpm - Dq) * p.alpha : 0.f;
         }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          st_tile_chunk(sP, r, c * 32 + g8 * 8, &pd[g8 * 8]);
-          st_tile_chunk(sDS, r, c * 32 + g8 * 8, &ds[g8 * 8]);
-        }
+        st_tile_chunk(sP, r, ch * 64 + c * 16, &pd[0]);
+        st_tile_chunk(sP, r, ch * 64 + c * 16 + 8, &pd[8]);
+        st_tile_chunk(sDS, r, ch * 64 + c * 16, &ds[0]);
+        st_tile_chunk(sDS, r, ch * 64 + c * 16 + 8, &ds[8]);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
       ptx::mbar_arrive(pds_full);
-      // dQ of this tile: TMEM -> fp32 vector atomics (the other key blocks of this image/head add to the same rows)
+      // dQ of this tile (this warp's 32 of the 64 columns): TMEM -> fp32 vector atomics (the other key blocks of this
+      // image/head add to the same rows)
       ptx::mbar_wait(dq_full, ((uint32_t)i) & 1u, 980);
       ptx::tc_fence_after();
-      float* dq = p.dQacc + ((long long)b * p.Lq + q) * p.lddq + h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      float* dq = p.dQacc + ((long long)b * p.Lq + q) * p.lddq + h * 64 + ch * 32;
+      {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(tdQ + lane_off + (uint32_t)(c * 32), v);
+        ptx::tmem_ld_32x32(tdQ + lane_off + (uint32_t)(ch * 32), v);
         ptx::tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4)
-            atomicAdd(reinterpret_cast<float4*>(dq + c * 32 + g4 * 4),
+            atomicAdd(reinterpret_cast<float4*>(dq + g4 * 4),
                       make_float4(__uint_as_float(v[g4 * 4]), __uint_as_float(v[g4 * 4 + 1]),
                                   __uint_as_float(v[g4 * 4 + 2]), __uint_as_float(v[g4 * 4 + 3])));
         }
@@ -446,29 +467,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     const int key = k0 + r;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = which == 0 ? p.dV + ((long long)b * p.Lk + key) * p.lddv + h * 64
-                                      : p.dK + ((long long)b * p.Lk + key) * p.lddk + h * 64;
+      __nv_bfloat16* dst = (which == 0 ? p.dV + ((long long)b * p.Lk + key) * p.lddv : p.dK + ((long long)b * p.Lk + key) * p.lddk) +
+                           h * 64 + ch * 32;
       const uint32_t tsrc = which == 0 ? tdV : tdK;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tsrc + lane_off + (uint32_t)(c * 32), v);
-        ptx::tmem_ld_wait();
-        if (key < p.Lk) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tsrc + lane_off + (uint32_t)(ch * 32), v);
+      ptx::tmem_ld_wait();
+      if (key < p.Lk) {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float o[8];
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g8 * 8 + j]);
-            st8(dst + c * 32 + g8 * 8, o);
-          }
+          for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g8 * 8 + j]);
+          st8(dst + g8 * 8, o);
         }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem);
   }

@@ -54,13 +54,19 @@ __device__ __forceinline__ void st4x(void* base, long long idx, int fp32, const 
 }
 
 // counter-based dropout RNG: keep iff hash(seed, index) >= p * 2^32.  The mask is a pure function of
-// (seed, element index) so backward regenerates it instead of storing it.
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return (uint32_t)x;
+// (seed, element index) so backward regenerates it instead of storing it.  The hash is murmur3's 32-bit finaliser
+// over a 32-bit fold of (index, seed): ~10 integer instructions per element (the seed terms are loop invariant).
+// The 64-bit splitmix variant used before cost ~25 and made the fused attention's softmax phase issue-bound.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {  // kept for callers that want one 32-bit word per 64-bit key
+  return fmix32((uint32_t)x * 0x9E3779B1u + (uint32_t)(x >> 32) * 0x7FEB352Du);
 }
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-  return mix32(seed * 0x9E3779B97F4A7C15ULL + idx) >= thresh;
+  const uint32_t s = (uint32_t)seed * 0x27D4EB2Fu + (uint32_t)(seed >> 32) * 0x846CA68Bu;
+  return fmix32((uint32_t)idx * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x7FEB352Du + s) >= thresh;
 }
 __host__ __device__ inline uint32_t drop_thresh(float p) {
   double t = (double)p * 4294967296.0;
