@@ -26,6 +26,12 @@ for part in $PARTS; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:bn_stream -c 6 -f \
         -o gpurun_out/${TAG}_bn_stream python tools/bn_bench.py --stream 1 --once > gpurun_out/${TAG}_ncu_bn.log 2>&1
       echo "[ncu_bn] rc=$?" ;;
+    attnbench)
+      timeout 200 python tools/attn_bench.py > gpurun_out/${TAG}_attnbench.log 2>&1
+      echo "[attnbench] rc=$?"; cat gpurun_out/${TAG}_attnbench.log
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 3 -f \
+        -o gpurun_out/${TAG}_attn python tools/attn_bench.py --once > gpurun_out/${TAG}_ncu_attn.log 2>&1
+      echo "[ncu_attn] rc=$?" ;;
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
