@@ -19,10 +19,11 @@
 //   dQ_i = dS K (TMEM -> fp32 vector atomics into the dQ accumulator, 6 key blocks add into one row).
 //   The P / dS tiles are written once as [query][key] and read by the tensor core both K-major (dQ) and MN-major
 //   (the transposed products dV, dK): no transposition pass.
-// Warp roles (320 threads): warps 0-7 softmax + epilogue — warp w owns TMEM lanes 32*(w%4).. (one row per thread)
-// and the column half w/4 of every 128-column block, so every scheduler has softmax work (the phase is
-// instruction-issue bound: exp2 + dropout hash + bf16 pack per score); warp 8 TMA producer; warp 9 TMEM allocator +
-// single-thread MMA issuer.
+// Warp roles: NSW softmax + epilogue warps (forward 8, two CTAs per SM; backward 16, one CTA per SM) — warp w owns
+// TMEM lanes 32*(w%4).. (one row per thread) and the column slice w/4 of every 128-column block, so every scheduler
+// has several softmax warps (the phase is instruction-issue bound: exp2 + dropout hash + bf16 pack per score; the
+// hash is shared by column pairs and interior tiles skip the edge masks); then one TMA producer warp and one TMEM
+// allocator + single-thread MMA issuer warp.
 #include <cudaTypedefs.h>
 
 #include <mutex>
@@ -32,15 +33,18 @@
 
 namespace cris {
 
-constexpr int AT_THREADS = 320;
-constexpr int AT_SM_THREADS = 256;  // softmax / epilogue threads (warps 0-7)
+constexpr int AT_THREADS = 320;       // forward: 8 softmax warps + producer + MMA
+constexpr int AT_SM_THREADS = 256;
+constexpr int ATB_SW = 16;            // backward: 16 softmax warps (4 column quarters)
+constexpr int ATB_SM_THREADS = ATB_SW * 32;
+constexpr int ATB_THREADS = ATB_SM_THREADS + 64;
 constexpr int AT_TILE = 16384;  // 128 rows x 64 bf16 = one 128B-swizzled box
 
 struct AttnArgs {
   int B, heads, Lq, Lk, LkPad;
   float scale_log2;  // alpha * log2(e): t = s * scale_log2 lives in the log2 domain
   float alpha;
-  uint32_t drop_thresh;
+  uint32_t drop_thresh;  // 16-bit threshold (drop_thresh16), 0 = no dropout
   float inv_keep;    // 1 / (1 - p_drop)
   uint64_t seed;
   const uint64_t* seed_dev;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     const int q = q0 + r;
     uint64_t seed = p.seed;
     if (p.seed_dev != nullptr) seed += *p.seed_dev;
-    const uint64_t row_idx = ((uint64_t)(b * p.heads + h) * (uint64_t)p.Lq + (uint64_t)q) * (uint64_t)p.LkPad;
+    const uint32_t rh = drop_row_hash(seed, (uint64_t)(b * p.heads + h) * (uint64_t)p.Lq + (uint64_t)q);
     uint8_t* sP = smem + FwdSmem::P;
     float m = -INFINITY;
     int ns = 0;
@@ -199,13 +203,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       ptx::tc_fence_after();
       const int valid = p.Lk - j * 128 - ch * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(ch * 64 + c * 16), v);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tS + lane_off + (uint32_t)(ch * 64 + c * 32), v);
         ptx::tmem_ld_wait();
+        if (valid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c * 16 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) m = fmaxf(m, __uint_as_float(v[i]));
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
@@ -228,16 +237,22 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         ptx::tmem_ld_wait();
         float e[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mt));
-          e[i] = (c * 16 + i < valid) ? x : 0.f;
-          l += e[i];
-        }
-        if (p.drop_thresh != 0u) {
-          const uint64_t base = row_idx + (uint64_t)(j * 128 + ch * 64 + c * 16);
+        for (int i = 0; i < 16; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mt));
+        if (valid < 64) {                       // ragged last key block only
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (!drop_keep(seed, base + (uint64_t)i, p.drop_thresh)) e[i] = 0.f;
+            if (!(c * 16 + i < valid)) e[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) l += e[i];
+        if (p.drop_thresh != 0u) {
+          const uint32_t pair0 = (uint32_t)(j * 128 + ch * 64 + c * 16) >> 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t hb = drop_pair_bits(rh, pair0 + (uint32_t)i);
+            if ((hb & 0xffffu) < p.drop_thresh) e[2 * i] = 0.f;
+            if ((hb >> 16) < p.drop_thresh) e[2 * i + 1] = 0.f;
+          }
         }
         st_tile_chunk(sP, r, ch * 64 + c * 16, &e[0]);
         st_tile_chunk(sP, r, ch * 64 + c * 16 + 8, &e[8]);
@@ -306,7 +321,7 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long l
   if (lane == 0) D[wid] = s;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(ATB_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnArgs p) {
   extern __shared__ uint8_t at_smem_raw[];
@@ -330,24 +345,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&qd_full[s], 1); ptx::mbar_init(&qd_empty[s], 1); }
     ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(s_empty, AT_SM_THREADS);
-    ptx::mbar_init(pds_full, AT_SM_THREADS);
+    ptx::mbar_init(s_empty, ATB_SM_THREADS);
+    ptx::mbar_init(pds_full, ATB_SM_THREADS);
     ptx::mbar_init(pds_empty, 1);
     ptx::mbar_init(dq_full, 1);
-    ptx::mbar_init(dq_empty, AT_SM_THREADS);
+    ptx::mbar_init(dq_empty, ATB_SM_THREADS);
     ptx::fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == ATB_SW && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
   }
-  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == ATB_SW + 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
-  if (warp == 8) {
+  if (warp == ATB_SW) {
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
       ptx::tma_load_4d(smem + BwdSmem::K, &tmK, kv_full, 0, k0, h, b);
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         ptx::tma_load_4d(smem + BwdSmem::QD + s * 2 * AT_TILE + AT_TILE, &tmdO, &qd_full[s], 0, i * 128, h, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == ATB_SW + 1) {
     if (lane == 0) {
       constexpr uint32_t idS = ptx::make_idesc_bf16(128, 128, 0, 0);   // Q K^T, dO V^T
       constexpr uint32_t idT = ptx::make_idesc_bf16(128, 64, 1, 1);    // Pd^T dO, dS^T Q
@@ -397,63 +412,77 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       }
     }
   } else {
-    // thread = (query row r, column half ch) as in the forward; for the dK/dV epilogue r is the key row
-    const int quad = warp & 3, ch = warp >> 2;
+    // thread = (query row r, column quarter cq): 32 of the 128 key columns; for the dK/dV epilogue r is the key row
+    const int quad = warp & 3, cq = warp >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     uint64_t seed = p.seed;
     if (p.seed_dev != nullptr) seed += *p.seed_dev;
     uint8_t* sP = smem + BwdSmem::P;
     uint8_t* sDS = smem + BwdSmem::DS;
-    const int valid = p.Lk - k0 - ch * 64;  // keys of this thread's column half that exist
+    const int valid = p.Lk - k0 - cq * 32;  // keys of this thread's column quarter that exist
     const size_t bh = (size_t)(b * p.heads + h);
     for (int i = 0; i < nq; ++i) {
       const int q = i * 128 + r;
       const bool row_ok = q < p.Lq;
+      const bool interior = (i * 128 + 128 <= p.Lq) && (k0 + 128 <= p.Lk);  // CTA-uniform: no edge masks needed
       const float lse = row_ok ? p.lse[bh * p.Lq + q] : 0.f;
       const float Dq = row_ok ? p.Dsum[bh * p.Lq + q] : 0.f;
-      const uint64_t row_idx = (bh * (uint64_t)p.Lq + (uint64_t)q) * (uint64_t)p.LkPad + (uint64_t)(k0 + ch * 64);
+      const uint32_t rh = drop_row_hash(seed, bh * (uint64_t)p.Lq + (uint64_t)q);
       ptx::mbar_wait(sdp_full, ((uint32_t)i) & 1u, 960);
       if (i > 0) ptx::mbar_wait(pds_empty, ((uint32_t)(i - 1)) & 1u, 970);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t sv[16], dv[16];
-        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(ch * 64 + c * 16), sv);
-        ptx::tmem_ld_32x16(tdP + lane_off + (uint32_t)(ch * 64 + c * 16), dv);
+        ptx::tmem_ld_32x16(tS + lane_off + (uint32_t)(cq * 32 + c * 16), sv);
+        ptx::tmem_ld_32x16(tdP + lane_off + (uint32_t)(cq * 32 + c * 16), dv);
         ptx::tmem_ld_wait();
         float pd[16], ds[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const bool ok = row_ok && (c * 16 + j < valid);
-          const float pr = ok ? fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse)) : 0.f;
-          bool keep = true;
-          if (p.drop_thresh != 0u) keep = drop_keep(seed, row_idx + (uint64_t)(c * 16 + j), p.drop_thresh);
-          const float dpm = keep ? __uint_as_float(dv[j]) * p.inv_keep : 0.f;
-          pd[j] = keep ? pr * p.inv_keep : 0.f;
-          ds[j] = ok ? pr * (dpm - Dq) * p.alpha : 0.f;
+        for (int j = 0; j < 16; ++j) pd[j] = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
+        if (!interior) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (!(row_ok && (c * 16 + j < valid))) pd[j] = 0.f;
         }
-        st_tile_chunk(sP, r, ch * 64 + c * 16, &pd[0]);
-        st_tile_chunk(sP, r, ch * 64 + c * 16 + 8, &pd[8]);
-        st_tile_chunk(sDS, r, ch * 64 + c * 16, &ds[0]);
-        st_tile_chunk(sDS, r, ch * 64 + c * 16 + 8, &ds[8]);
+        if (p.drop_thresh != 0u) {
+          const uint32_t pair0 = (uint32_t)(k0 + cq * 32 + c * 16) >> 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t hb = drop_pair_bits(rh, pair0 + (uint32_t)j);
+            const bool k0_ = (hb & 0xffffu) >= p.drop_thresh, k1_ = (hb >> 16) >= p.drop_thresh;
+            // ds = alpha * P * (dropout'(dP) - D);  pd = dropout(P)
+            ds[2 * j] = pd[2 * j] * ((k0_ ? __uint_as_float(dv[2 * j]) * p.inv_keep : 0.f) - Dq) * p.alpha;
+            ds[2 * j + 1] = pd[2 * j + 1] * ((k1_ ? __uint_as_float(dv[2 * j + 1]) * p.inv_keep : 0.f) - Dq) * p.alpha;
+            pd[2 * j] = k0_ ? pd[2 * j] * p.inv_keep : 0.f;
+            pd[2 * j + 1] = k1_ ? pd[2 * j + 1] * p.inv_keep : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ds[j] = pd[j] * (__uint_as_float(dv[j]) - Dq) * p.alpha;
+        }
+        st_tile_chunk(sP, r, cq * 32 + c * 16, &pd[0]);
+        st_tile_chunk(sP, r, cq * 32 + c * 16 + 8, &pd[8]);
+        st_tile_chunk(sDS, r, cq * 32 + c * 16, &ds[0]);
+        st_tile_chunk(sDS, r, cq * 32 + c * 16 + 8, &ds[8]);
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(s_empty);
       ptx::mbar_arrive(pds_full);
-      // dQ of this tile (this warp's 32 of the 64 columns): TMEM -> fp32 vector atomics (the other key blocks of this
+      // dQ of this tile (this warp's 16 of the 64 columns): TMEM -> fp32 vector atomics (the other key blocks of this
       // image/head add to the same rows)
       ptx::mbar_wait(dq_full, ((uint32_t)i) & 1u, 980);
       ptx::tc_fence_after();
-      float* dq = p.dQacc + ((long long)b * p.Lq + q) * p.lddq + h * 64 + ch * 32;
+      float* dq = p.dQacc + ((long long)b * p.Lq + q) * p.lddq + h * 64 + cq * 16;
       {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tdQ + lane_off + (uint32_t)(ch * 32), v);
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(tdQ + lane_off + (uint32_t)(cq * 16), v);
         ptx::tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4)
+          for (int g4 = 0; g4 < 4; ++g4)
             atomicAdd(reinterpret_cast<float4*>(dq + g4 * 4),
                       make_float4(__uint_as_float(v[g4 * 4]), __uint_as_float(v[g4 * 4 + 1]),
                                   __uint_as_float(v[g4 * 4 + 2]), __uint_as_float(v[g4 * 4 + 3])));
@@ -468,14 +497,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* dst = (which == 0 ? p.dV + ((long long)b * p.Lk + key) * p.lddv : p.dK + ((long long)b * p.Lk + key) * p.lddk) +
-                           h * 64 + ch * 32;
+                           h * 64 + cq * 16;
       const uint32_t tsrc = which == 0 ? tdV : tdK;
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tsrc + lane_off + (uint32_t)(ch * 32), v);
+      uint32_t v[16];
+      ptx::tmem_ld_32x16(tsrc + lane_off + (uint32_t)(cq * 16), v);
       ptx::tmem_ld_wait();
       if (key < p.Lk) {
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
+        for (int g8 = 0; g8 < 2; ++g8) {
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[g8 * 8 + j]);
@@ -486,7 +515,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == ATB_SW + 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem);
   }
@@ -532,7 +561,7 @@ static int fill_args(AttnArgs& a, int B, int heads, int Lq, int Lk, float alpha,
   a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.LkPad = (Lk + 7) / 8 * 8;
   a.alpha = alpha;
   a.scale_log2 = alpha * 1.4426950408889634f;
-  a.drop_thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  a.drop_thresh = p_drop > 0.f ? drop_thresh16(p_drop) : 0u;
   a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.seed = seed; a.seed_dev = seed_dev;
   return 0;
@@ -591,7 +620,7 @@ int cris_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
   a.dV = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
   CRIS_SET_SMEM_ONCE(attn_bwd_kernel, BwdSmem::BYTES);
   dim3 grid((Lk + 127) / 128, heads, B);
-  attn_bwd_kernel<<<grid, AT_THREADS, BwdSmem::BYTES, s>>>(tq, tk, tv, tdo, a);
+  attn_bwd_kernel<<<grid, ATB_THREADS, BwdSmem::BYTES, s>>>(tq, tk, tv, tdo, a);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256)
     }
   sum = warp_sum(sum);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  const uint32_t th = drop_thresh(p_drop);
+  const uint32_t th = drop_thresh16(p_drop);
+  const uint32_t rh = drop_row_hash(seed, (uint64_t)rid);  // same (row, column) masks as csrc/attention.cu
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         pr[i] = v[e][i] * inv;
-        pd[i] = (Pd != nullptr && drop_keep(seed, (uint64_t)(off + j0 + i), th)) ? pr[i] * keep_scale : 0.f;
+        pd[i] = (Pd != nullptr && drop_keep_rc(rh, (uint32_t)(j0 + i), th)) ? pr[i] * keep_scale : 0.f;
       }
       st8(P + off + j0, pr);
       if (Pd != nullptr) st8(Pd + off + j0, pd);
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(256)
   if (rid >= (long long)nb * Lq) return;
   const int bi = (int)(rid / Lq), qi = (int)(rid % Lq);
   const long long off = (long long)bi * batch_stride + (long long)qi * ld;
-  const uint32_t th = drop_thresh(p_drop);
+  const uint32_t th = drop_thresh16(p_drop);
+  const uint32_t rh = drop_row_hash(seed, (uint64_t)rid);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   float pv[NV][8], dv[NV][8];
   float dot = 0.f;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (j0 + i >= Lk) { pv[e][i] = 0.f; dv[e][i] = 0.f; }
-        else if (p_drop > 0.f) dv[e][i] = drop_keep(seed, (uint64_t)(off + j0 + i), th) ? dv[e][i] * keep_scale : 0.f;
+        else if (p_drop > 0.f) dv[e][i] = drop_keep_rc(rh, (uint32_t)(j0 + i), th) ? dv[e][i] * keep_scale : 0.f;
         dot += pv[e][i] * dv[e][i];
       }
     }

@@ -68,6 +68,24 @@ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t 
   const uint32_t s = (uint32_t)seed * 0x27D4EB2Fu + (uint32_t)(seed >> 32) * 0x846CA68Bu;
   return fmix32((uint32_t)idx * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x7FEB352Du + s) >= thresh;
 }
+// Row/column form for 2-D score matrices (attention dropout): one hash per row, then one fmix32 per column PAIR —
+// each column uses 16 bits of it (keep iff bits >= p * 2^16; p = 0.1 -> 6554 / 65536).  ~5 integer instructions per
+// element instead of ~10.  cris_softmax_* and the fused attention kernels share this, so they draw the same masks.
+__device__ __forceinline__ uint32_t drop_row_hash(uint64_t seed, uint64_t row) {
+  const uint32_t s = (uint32_t)seed * 0x27D4EB2Fu + (uint32_t)(seed >> 32) * 0x846CA68Bu;
+  return fmix32((uint32_t)row * 0x9E3779B1u + (uint32_t)(row >> 32) * 0x7FEB352Du + s);
+}
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t row_hash, uint32_t col_pair) {  // col_pair = col >> 1
+  return fmix32(row_hash + col_pair * 0x9E3779B1u);
+}
+__device__ __forceinline__ bool drop_keep_rc(uint32_t row_hash, uint32_t col, uint32_t thresh16) {
+  const uint32_t h = drop_pair_bits(row_hash, col >> 1);
+  return ((col & 1u) ? (h >> 16) : (h & 0xffffu)) >= thresh16;
+}
+__host__ __device__ inline uint32_t drop_thresh16(float p) {
+  const double t = (double)p * 65536.0 + 0.5;
+  return t >= 65535.0 ? 65535u : (uint32_t)t;
+}
 __host__ __device__ inline uint32_t drop_thresh(float p) {
   double t = (double)p * 4294967296.0;
   return t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
