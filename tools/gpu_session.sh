@@ -32,6 +32,19 @@ for part in $PARTS; do
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 3 -f \
         -o gpurun_out/${TAG}_attn python tools/attn_bench.py --once > gpurun_out/${TAG}_ncu_attn.log 2>&1
       echo "[ncu_attn] rc=$?" ;;
+    ddp2|ddp4|ddp8)
+      N=${part#ddp}
+      for cfg in "default" "CRIS_B200_BWD_SEGMENTS=3" "CRIS_B200_FUSED_SYNCBN=0"; do
+        envs=""; [ "$cfg" != "default" ] && envs="$cfg"
+        env $envs timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 \
+          bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-cpu-baseline --no-incumbent > gpurun_out/${TAG}_ddp${N}_${cfg%%=*}.json 2> gpurun_out/${TAG}_ddp${N}.err
+        echo "[ddp$N $cfg] rc=$?"; python -c "
+import json,sys
+try:
+    d=json.loads(open('gpurun_out/${TAG}_ddp${N}_${cfg%%=*}.json').read().strip().splitlines()[-1]); print('   ', d['value'], 'img/s', d['ms_per_step'], 'ms/step  e2e', d['e2e']['value'])
+except Exception as e: print('   parse error', e)
+"
+      done; tail -3 gpurun_out/${TAG}_ddp${N}.err ;;
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
