@@ -45,6 +45,11 @@ try:
 except Exception as e: print('   parse error', e)
 "
       done; tail -3 gpurun_out/${TAG}_ddp${N}.err ;;
+    ddpbreak2|ddpbreak4|ddpbreak8)
+      N=${part#ddpbreak}
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
+        tools/ddp_breakdown.py > gpurun_out/${TAG}_ddpbreak${N}.log 2>&1
+      echo "[ddpbreak$N] rc=$?"; grep -E "fwd|FAILED" gpurun_out/${TAG}_ddpbreak${N}.log ;;
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
