@@ -242,6 +242,22 @@ class CRIS(nn.Module):
         self._engine = None
 
     # ------------------------------------------------------------------------------------------
+    @property
+    def _ddp_params_and_buffers_to_ignore(self):
+        """Read by DistributedDataParallel at construction (torch/nn/parallel/distributed.py: names listed here are left
+        out of its parameter reduction and of the per-forward buffer broadcast).  When EVERY BatchNorm of the tree is a
+        SyncBatchNorm (train.py:97-98 converts before it wraps, :100-102) the running statistics are computed from the
+        same rank-ordered global sums with the same arithmetic on every rank, i.e. they are bit-identical already, and
+        DDP's default `broadcast_buffers=True` re-broadcast of all 213 buffers before every forward (coalesce + NCCL
+        broadcast + 213 copy-back kernels, ~1.5 ms per step, profiles/r02_ddp_breakdown_n2.txt) is a no-op — so those
+        buffers are listed.  With plain BatchNorm modules nothing is listed and DDP keeps rank 0's statistics
+        authoritative exactly as it does for the reference."""
+        bns = [m for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+        if not bns or not all(isinstance(m, nn.SyncBatchNorm) for m in bns):
+            return []
+        return [k for k, _ in self.named_buffers()
+                if k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+
     def _get_engine(self):
         if self._engine is None:
             from .engine import Engine

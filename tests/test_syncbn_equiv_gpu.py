@@ -64,10 +64,14 @@ def _worker(rank, world, port, q):
         dist.all_reduce(ld)
         grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
         used_peer = eng.peer_exchange(dev) is not None
-        q.put((rank, "ok", float(ld) / world, _summary(grads) if rank == 0 else None, used_peer, bool(eng.graphs)))
+        # running statistics must be bit-identical on every rank (DDP's per-forward buffer broadcast is skipped for them:
+        # CRIS._ddp_params_and_buffers_to_ignore)
+        stats = torch.cat([b.detach().double().reshape(-1).cpu() for k, b in model.named_buffers() if "running_" in k])
+        digest = (float(stats.sum()), float((stats * stats).sum()), float(stats.abs().max()))
+        q.put((rank, "ok", float(ld) / world, _summary(grads) if rank == 0 else None, used_peer, bool(eng.graphs), digest))
         dist.barrier()
     except Exception as e:  # surface worker failures instead of a queue timeout
-        q.put((rank, "error", repr(e), None, False, False))
+        q.put((rank, "error", repr(e), None, False, False, None))
         raise
     finally:
         dist.destroy_process_group()
@@ -116,6 +120,7 @@ def test_two_ranks_syncbn_ddp_equal_one_gpu_global_batch(golden_dir):
     for p in procs:
         p.join(timeout=120)
     assert all(r[1] == "ok" for r in res), res
+    assert res[0][6] == res[1][6], ("BatchNorm running statistics differ between the ranks", res[0][6], res[1][6])
     r0 = next(r for r in res if r[0] == 0)
     loss2, multi = r0[2], r0[3]
     print(f"loss 1x8 {loss1:.6f} / {loss1b:.6f}  2x4 {loss2:.6f}  peer exchange {r0[4]}  graphs {r0[5]}")
