@@ -277,6 +277,19 @@ int cris_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int heads, int Lq, int Lk,
                        float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream);
 
+/* ---- evaluation post-processing (SURVEY 8f "next" row 2; engine/engine.py:101-124,172-190): logits -> IoU against the
+ *      ground truth of the ORIGINAL photo.  cris_postproc_upsample: prob_up[b] = bicubic(sigmoid(logits[b]), align_corners
+ *      = True) (F.interpolate semantics), fp32 [B,H,W] -> [B,OH,OW].  cris_postproc_warp_iou: per sample the
+ *      cv2.warpAffine(prob_up, m, (w,h), INTER_CUBIC, borderValue 0) of the reference (fixed-point 1/32-pixel
+ *      coordinates, float cubic table), `> thr`, and counts[b] = {sum(pred & gt), sum(pred | gt)} (u64, zeroed by the
+ *      caller).  samples_dev: DEVICE array of B records {double m[6]; int h, w; int64 off} (cris_postproc_sample_bytes()
+ *      each; m is the matrix the reference passes to warpAffine, off the sample's offset into the packed uint8 buffers
+ *      gt / pred_out); pred_out (optional) receives the binary prediction; max_pixels = max over samples of h*w. */
+int cris_postproc_sample_bytes(void);
+int cris_postproc_upsample(const float* logits, float* prob_up, int B, int H, int W, int OH, int OW, void* stream);
+int cris_postproc_warp_iou(const float* prob_up, int B, int SH, int SW, const void* samples_dev, const uint8_t* gt,
+                           uint8_t* pred_out, float thr, unsigned long long* counts, long long max_pixels, void* stream);
+
 /* ---- optimizer step (SURVEY 8f "next" row: torch.optim.Adam driven by GradScaler, train.py:105-111,
  *      engine/engine.py:52-57).  One launch updates every tensor of a parameter group:
  *      g' = g / *grad_scale (+ weight_decay * p); m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
