@@ -9,7 +9,7 @@
 // changes is the data movement.  Those kernels keep their loads in registers (128 registers -> 2 blocks / SM ->
 // ~49 KB in flight per SM) and ran at 3.0-4.3 TB/s.  Here one warp issues bulk asynchronous copies
 // (cp.async.bulk global -> shared, completion on an mbarrier) of whole row tiles, STAGES tiles ahead: bytes in
-// flight are decoupled from registers (3 blocks x 2 tiles x up to 24 KB per SM), the 256 consumer threads read the
+// flight are decoupled from registers (2 blocks x 3 tiles x up to 24 KB per SM), the 256 consumer threads read the
 // tile with conflict-free 16-byte shared loads, and results leave through coalesced 16-byte stores.
 // Every operand is a [rows, C] bf16 row matrix with its own pitch (dense, or a column slice of a concat buffer:
 // then the tile is fetched row by row).  C must be a power of two >= 8 (every BatchNorm of the model).
@@ -19,7 +19,8 @@
 namespace cris {
 
 constexpr int BS_THREADS = 256;
-constexpr int BS_STAGES = 3;       // 3 stages x 3 operands x 8 KB = 72 KB per block -> three blocks (24 warps) per SM
+constexpr int BS_STAGES = 4;       // 4 stages x 3 operands x 8 KB = 96 KB per block, two blocks per SM (measured: three
+                                   // blocks with 3 stages is slower, profiles/r02_bn_bench.txt)
 constexpr int BS_TILE_BYTES = 8192;   // per operand and stage
 constexpr int BS_MAX_OPS = 3;
 
@@ -94,12 +95,10 @@ __device__ __forceinline__ void ld8s(const uint8_t* tile, int item, float* v) {
 
 // KIND 0: forward apply   1: reduction   2: backward apply
 template <int KIND>
-__global__ void __launch_bounds__(BS_THREADS, 3) bn_stream_kernel(const BsArgs p) {
+__global__ void __launch_bounds__(BS_THREADS, 2) bn_stream_kernel(const BsArgs p) {
   extern __shared__ __align__(128) uint8_t bs_smem[];
   __shared__ uint64_t full[BS_STAGES];
-  // the cross-row-lane reduction of KIND 1 reuses the (by then idle) tile buffers: no static shared memory, so the
-  // three kinds all fit three blocks per SM (the passes are instruction-issue bound — ncu: issue active ~50 % with
-  // 16 warps per SM — so resident warps, not bytes in flight, are what buys bandwidth)
+  // the cross-row-lane reduction of KIND 1 reuses the (by then idle) tile buffers: no static shared memory
   float* red = reinterpret_cast<float*>(bs_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = 1 << p.logG;
