@@ -347,7 +347,7 @@ def main():
         scaler.scale(loss).backward()                         # :53
         scaler.step(opt)                                      # :56
         scaler.update()                                       # :57
-        iou, pr5 = train_metric(pred, tgt)                    # :60
+        iou, pr5 = bare.train_metric()                        # :60 trainMetricGPU, counts fused into the loss kernel
         ld = loss.detach()
         if world > 1:                                         # :61-63
             dist.all_reduce(ld); dist.all_reduce(iou); dist.all_reduce(pr5)
@@ -383,6 +383,12 @@ def main():
     for _ in range(args.warmup):
         step(img_d, word_d, mask_d)
     torch.cuda.synchronize()
+    # the fused metric is the reference's trainMetricGPU: check it once against the torch restatement of utils/misc.py
+    with torch.no_grad():
+        p_chk, t_chk, _ = model(img_d, word_d, mask_d)
+        a, b_ = bare.train_metric()
+        c, d = train_metric(p_chk, t_chk)
+        assert abs(float(a) - float(c)) < 0.05 and abs(float(b_) - float(d)) < 2.0, (float(a), float(c), float(b_), float(d))
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     ms_total, last = timed(args.steps, from_host=False)

@@ -79,7 +79,7 @@ _SIGS = {
     "cris_pack_matrix": "ppqiip",
     "cris_batch_reduce": "piqpqiiiip",
     "cris_small_matmul": "pppiiiiip",
-    "cris_dynconv_bce_fwd": "pqpqpiipppiiiip",
+    "cris_dynconv_bce_fwd": "pqpqpiippppfiiiip",
     "cris_dynconv_bce_bwd": "pqpqpppppqpqiiiip",
     "cris_adam_step": "piqddddddppp",
     "cris_postproc_upsample": "ppiiiiip",

@@ -26,9 +26,11 @@ __global__ void __launch_bounds__(256)
     dynconv_bce_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ t,
                            long long ldt, const float* __restrict__ mask, int Hm, int Wm, float* __restrict__ pred,
                            float* __restrict__ mask_out, float* __restrict__ loss_sum, int B, int H, int W, int C,
-                           float inv_n) {
+                           float inv_n, unsigned* __restrict__ metric_counts, float metric_thr) {
   extern __shared__ float sk[];  // [9][8][G]
   __shared__ float s_loss[8];
+  __shared__ unsigned s_cnt[8][2];
+  unsigned n_inter = 0, n_union = 0;  // trainMetricGPU (utils/misc.py:114-129) fused: sigmoid(pred) >= thr vs target != 0
   const int b = blockIdx.y;
   stage_kernel(t, ldt, b, C, sk);
   __syncthreads();
@@ -78,16 +80,21 @@ __global__ void __launch_bounds__(256)
         const float tg = mask[((long long)b * Hm + (long long)h * sh) * Wm + (long long)w * sw];
         mask_out[(long long)b * npix + p] = tg;
         lsum += fmaxf(acc, 0.f) - acc * tg + log1pf(__expf(-fabsf(acc)));
+        const bool o = (1.f / (1.f + expf(-acc))) >= metric_thr, g1 = tg != 0.f;
+        n_inter += (o && g1) ? 1u : 0u;
+        n_union += (o || g1) ? 1u : 0u;
       }
     }
   }
   if (mask != nullptr) {
-    if (lane == 0) s_loss[warp] = lsum;
+    if (lane == 0) { s_loss[warp] = lsum; s_cnt[warp][0] = n_inter; s_cnt[warp][1] = n_union; }
     __syncthreads();
     if (threadIdx.x == 0) {
       float s = 0.f;
-      for (int i = 0; i < 8; ++i) s += s_loss[i];
+      unsigned ci = 0, cu = 0;
+      for (int i = 0; i < 8; ++i) { s += s_loss[i]; ci += s_cnt[i][0]; cu += s_cnt[i][1]; }
       atomicAdd(loss_sum, s * inv_n);
+      if (metric_counts != nullptr) { atomicAdd(metric_counts + 2 * b, ci); atomicAdd(metric_counts + 2 * b + 1, cu); }
     }
   }
 }
@@ -216,7 +223,8 @@ extern "C" {
  * (c, ky, kx) order; mask: fp32 [B,1,Hm,Wm] or NULL (eval); pred/mask_out: fp32 [B,H,W]; loss_sum: fp32
  * scalar, must be zeroed by the caller. */
 int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt, const float* mask, int Hm, int Wm,
-                         float* pred, float* mask_out, float* loss_sum, int B, int H, int W, int C, void* stream) {
+                         float* pred, float* mask_out, float* loss_sum, unsigned* metric_counts, float metric_thr, int B,
+                         int H, int W, int C, void* stream) {
   CRIS_CHECK_ARG(C % 8 == 0 && 9 * C * 4 <= 96 * 1024, "dynconv: C=%d unsupported", C);
   CRIS_CHECK_ARG(mask == nullptr || (Hm % H == 0 && Wm % W == 0), "dynconv: mask %dx%d not an integer multiple", Hm, Wm);
   CRIS_SET_SMEM_ONCE(dynconv_bce_fwd_kernel<false>, 96 * 1024);
@@ -226,10 +234,10 @@ int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   if (C <= 256)
     dynconv_bce_fwd_kernel<true><<<grid, 256, 9 * C * 4, STREAM>>>(xb, ldx, t, ldt, mask, Hm, Wm, pred, mask_out,
-                                                                  loss_sum, B, H, W, C, inv_n);
+                                                                  loss_sum, B, H, W, C, inv_n, metric_counts, metric_thr);
   else
     dynconv_bce_fwd_kernel<false><<<grid, 256, 9 * C * 4, STREAM>>>(xb, ldx, t, ldt, mask, Hm, Wm, pred, mask_out,
-                                                                   loss_sum, B, H, W, C, inv_n);
+                                                                   loss_sum, B, H, W, C, inv_n, metric_counts, metric_thr);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -185,6 +185,7 @@ class Engine:
         # eval mode: BatchNorm folded into the producing convolution (weights x scale, shift as bias, residual + ReLU in
         # the GEMM epilogue) instead of a bn_coeffs + bn_apply pass per layer
         self.fold_eval_bn = os.environ.get("CRIS_B200_FOLD_EVAL_BN", "1") != "0"
+        self.last_metric_counts: Optional[torch.Tensor] = None  # int32 [B,2] of the last training forward
         self.graphs: Dict[tuple, "GraphedStep"] = {}
         self.eval_graphs: Dict[tuple, "GraphedEval"] = {}
         self._counter: Optional[torch.Tensor] = None
@@ -1492,10 +1493,14 @@ class Run:
         mask_out = torch.empty(B, 1, Ho, Wo, dtype=torch.float32, device=self.dev) if self.mask is not None else None
         loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         Hm, Wm = (self.mask.shape[-2], self.mask.shape[-1]) if self.mask is not None else (0, 0)
+        # per-sample intersection / union counts of (sigmoid(pred) >= 0.35) vs (target != 0): trainMetricGPU's reduction
+        # (utils/misc.py:114-129), taken inside the loss kernel; read through CRIS.train_metric()
+        counts = torch.zeros(B, 2, dtype=torch.int32, device=self.dev) if self.mask is not None else None
         call("cris_dynconv_bce_fwd", xf.ptr, xf.ld, t.ptr, t.ld, self.mask.data_ptr() if self.mask is not None else None,
-             Hm, Wm, pred.data_ptr(), mask_out.data_ptr() if mask_out is not None else None, loss.data_ptr(), B, Ho, Wo,
-             C)
-        self.pred, self.mask_out, self.loss = pred, mask_out, loss
+             Hm, Wm, pred.data_ptr(), mask_out.data_ptr() if mask_out is not None else None, loss.data_ptr(),
+             counts.data_ptr() if counts is not None else None, 0.35, B, Ho, Wo, C)
+        self.pred, self.mask_out, self.loss, self.metric_counts = pred, mask_out, loss, counts
+        self.e.last_metric_counts = counts
         self._head = (xf, t, B, Ho, Wo, C)
 
     # =================================================================================================

@@ -258,6 +258,17 @@ class CRIS(nn.Module):
         return [k for k, _ in self.named_buffers()
                 if k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
 
+    def train_metric(self, pr_iou: float = 0.5):
+        """(IoU, Pr@pr_iou) in percent of the LAST training forward — the numbers `trainMetricGPU(pred, target, 0.35,
+        0.5)` (utils/misc.py:114-129, called at engine/engine.py:60) returns, from the per-sample intersection / union
+        counts the loss kernel took while the logits were in registers (no extra pass over pred / target)."""
+        c = self._get_engine().last_metric_counts
+        if c is None:
+            raise RuntimeError("train_metric() needs a preceding training-mode forward")
+        c = c.float()
+        ious = c[:, 0] / (c[:, 1] + 1e-6)
+        return 100.0 * ious.mean(), 100.0 * (ious > pr_iou).float().mean()
+
     def _get_engine(self):
         if self._engine is None:
             from .engine import Engine

@@ -221,8 +221,12 @@ int cris_small_matmul(const float* R, const float* X, float* out, int M, int K, 
 
 /* ---- text-to-pixel head + loss (Projector grouped conv model/layers.py:71-84; nearest mask resize + BCE
  *      model/segmenter.py:56-59) ------------------------------------------------------------------------ */
+/* metric_counts (optional, u32 [B][2], zeroed by the caller): per-sample {sum(o & g), sum(o | g)} with
+ * o = sigmoid(pred) >= metric_thr, g = target != 0 — the counts trainMetricGPU (utils/misc.py:114-129) reduces, taken
+ * while the logits are still in registers */
 int cris_dynconv_bce_fwd(const void* x, int64_t ldx, const float* t, int64_t ldt, const float* mask, int Hm, int Wm,
-                         float* pred, float* mask_out, float* loss_sum, int B, int H, int W, int C, void* stream);
+                         float* pred, float* mask_out, float* loss_sum, unsigned* metric_counts, float metric_thr, int B,
+                         int H, int W, int C, void* stream);
 int cris_dynconv_bce_bwd(const void* x, int64_t ldx, const float* t, int64_t ldt, const float* pred,
                          const float* target, const float* g, float* dl, void* dx, int64_t lddx, float* dt,
                          int64_t lddt, int B, int H, int W, int C, void* stream);

@@ -473,8 +473,11 @@ def test_dynconv_bce(B, C, H, W):
     mo = torch.empty(B, 1, H, W, device="cuda")
     loss = torch.zeros((), device="cuda")
     mk = mask.cuda()
+    mk[0, 0, :8] = 0.0  # exact zeros in the target: `target.bool()` of trainMetricGPU must see them as background
+    mask = mk.cpu()
+    counts = torch.zeros(B, 2, dtype=torch.int32, device="cuda")
     call("cris_dynconv_bce_fwd", xm.ptr, xm.ld, tb.data_ptr(), ld, mk.data_ptr(), 4 * H, 4 * W, pred.data_ptr(),
-         mo.data_ptr(), loss.data_ptr(), B, H, W, C)
+         mo.data_ptr(), loss.data_ptr(), counts.data_ptr(), 0.35, B, H, W, C)
     xr = x.clone().requires_grad_(True)
     tr = t.clone().requires_grad_(True)
     kern, bias = tr[:, :-1].reshape(B, C, 3, 3), tr[:, -1]
@@ -486,6 +489,11 @@ def test_dynconv_bce(B, C, H, W):
     assert rel(pred.cpu(), ref.detach()) < 1e-3
     assert torch.equal(mo.cpu(), tgt)
     assert abs(float(loss) - float(rl)) < 1e-4
+    # fused trainMetricGPU counts (utils/misc.py:114-129) on the kernel's own logits
+    o = torch.sigmoid(pred.cpu().flatten(1)) >= 0.35
+    tgb = tgt.flatten(1).bool()
+    exp = torch.stack([(o & tgb).sum(1), (o | tgb).sum(1)], 1).int()
+    assert (counts.cpu() - exp).abs().max() <= 1  # a logit exactly at the threshold may round either way
     gs = torch.full((1,), 3.0, device="cuda")
     dl = torch.empty(B * H * W, device="cuda")
     dx = torch.empty(B * (H + 2) * (W + 2), C, dtype=torch.bfloat16, device="cuda")
