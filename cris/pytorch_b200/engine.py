@@ -349,6 +349,8 @@ class GraphedStep:
                     r.forward()
                 n1 = _lib.launch_count()
                 self.pred, self.mask_out, self.loss = r.pred, r.mask_out, r.loss
+                self.metric_counts = r.metric_counts
+                self.engine = engine
                 self.gbs, self.n_bwds = [], []
                 for k in range(len(self.seg_names)):
                     gb = torch.cuda.CUDAGraph()
@@ -428,6 +430,7 @@ class _GraphFunction(torch.autograd.Function):
             if t2 - t0 > 0.01:
                 print(f"[hostprof] input copies {1e3 * (t1 - t0):.1f} ms, graph launch {1e3 * (t2 - t1):.1f} ms", flush=True)
         _lib.lib().cris_add_launch_count(gs.n_fwd)
+        gs.engine.last_metric_counts = gs.metric_counts  # refilled by this replay (read by CRIS.train_metric())
         ctx.gs = gs
         # fresh tensors: the static capture buffers are overwritten by the next replay, and callers may keep
         # predictions / masks across iterations (metric accumulation), as they can with the reference
@@ -455,6 +458,7 @@ class _GraphFirst(torch.autograd.Function):
         gs.mask.copy_(mask)
         gs.gf.replay()
         _lib.lib().cris_add_launch_count(gs.n_fwd)
+        gs.engine.last_metric_counts = gs.metric_counts
         ctx.gs = gs
         pred, mask_out, loss = gs.pred.detach().clone(), gs.mask_out.detach().clone(), gs.loss.detach().clone()
         ctx.mark_non_differentiable(pred, mask_out)

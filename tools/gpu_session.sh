@@ -74,6 +74,12 @@ except Exception as e: print('   parse error', e)
     benchq)
       timeout 600 python bench.py --steps 10 --warmup 3 --no-incumbent --no-cpu-baseline > gpurun_out/${TAG}_benchq.json 2> gpurun_out/${TAG}_benchq.err
       echo "[benchq] rc=$?"; tail -c 5000 gpurun_out/${TAG}_benchq.json; tail -5 gpurun_out/${TAG}_benchq.err ;;
+    ncu_gemm)
+      for i in 3 6 11 13 14 15; do
+        timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -f \
+          -o gpurun_out/${TAG}_gemm_perf$i tests/native/gemm_selftest perf $i > gpurun_out/${TAG}_ncu_gemm$i.log 2>&1
+        echo "[ncu gemm perf $i] rc=$?"
+      done ;;
     ncu_wgrad)
       for i in 11 12 14; do
         timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -f \
