@@ -278,6 +278,45 @@ __global__ void pack_matrix_kernel(const float* __restrict__ w, __nv_bfloat16* _
     out[i] = f2bf(c < cols ? w[r * cols + c] * (row_scale != nullptr ? row_scale[r] : 1.f) : 0.f);
   }
 }
+// Every bf16 kernel-layout weight copy of the model refreshed by ONE launch (was one pack launch per parameter, 143 per
+// step): a device table of entries, block -> entry by binary search over chunk prefix sums (the multi-tensor Adam
+// kernel's scheme).  taps == 1: matrix [rows][cols] -> [rows][ld]; taps > 1: conv OIHW -> [Cout][taps][ld = cin_pad].
+struct PackEntry {
+  const float* src;
+  __nv_bfloat16* dst;
+  long long rows;     // output rows (Cout)
+  int cols;           // matrix: source columns; conv: Cin
+  int ld;             // destination pitch (matrix) / cin_pad (conv)
+  int taps;
+  int pad_;
+  long long chunk0;   // exclusive prefix sum of ceil(dst elements / kPackChunk)
+};
+constexpr int kPackChunk = 8192;
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackEntry* __restrict__ tab, int n) {
+  int lo = 0, hi = n - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].chunk0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackEntry e = tab[lo];
+  const long long total = e.rows * (long long)e.taps * e.ld;
+  const long long i0 = (b - e.chunk0) * kPackChunk, i1 = min(total, i0 + kPackChunk);
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int c = (int)(i % e.ld);
+    float v = 0.f;
+    if (e.taps == 1) {
+      const long long r = i / e.ld;
+      if (c < e.cols) v = e.src[r * e.cols + c];
+    } else {
+      const int t = (int)((i / e.ld) % e.taps);
+      const long long co = i / ((long long)e.ld * e.taps);
+      if (c < e.cols) v = e.src[(co * e.cols + c) * e.taps + t];
+    }
+    e.dst[i] = f2bf(v);
+  }
+}
 // out[t, c] (+)= sum_b in[b*T + t, c]   (batch reduction of token gradients -> shared positional term)
 __global__ void batch_reduce_kernel(const void* __restrict__ in, int in_fp32, long long ldin, float* __restrict__ out,
                                     long long ldo, int B, int T, int C, int accumulate) {
@@ -403,6 +442,15 @@ int cris_elementwise(int op, const void* a, int a_fp32, int64_t lda, const void*
 int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps, int cin_pad, void* stream) {
   pack_conv_weight_kernel<<<grid_for((long long)Cout * taps * cin_pad, 256), 256, 0, STREAM>>>(w, BF(out), Cout, Cin,
                                                                                              taps, cin_pad);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_pack_entry_bytes(void) { return (int)sizeof(PackEntry); }
+int cris_pack_chunk_elems(void) { return kPackChunk; }
+int cris_pack_multi(const void* table_dev, int n_entries, long long n_chunks, void* stream) {
+  CRIS_CHECK_ARG(table_dev != nullptr && n_entries >= 1 && n_chunks >= 1 && n_chunks < (1ll << 31),
+                 "cris_pack_multi: bad table (%d entries, %lld chunks)", n_entries, n_chunks);
+  pack_multi_kernel<<<(unsigned)n_chunks, 256, 0, STREAM>>>(static_cast<const PackEntry*>(table_dev), n_entries);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -78,6 +78,39 @@ class PackedWeights:
         self.force = False        # CUDA-graph capture: always (re)launch the pack kernel into the cached buffer
         self.done_in_pass = set()  # ... but only once per captured pass
 
+    def refresh_all(self) -> bool:
+        """Re-pack EVERY cached copy with one kernel launch (csrc/tokens.cu pack_multi_kernel) and mark them done for
+        this pass — used inside CUDA-graph captures, where every copy must be refreshed on every replay (one launch
+        instead of ~143).  The device table is rebuilt only when a source / destination pointer changed."""
+        ents = [(k, v) for k, v in self.cache.items() if not k.endswith("#folded") and len(v) == 3]
+        if not ents:
+            return False
+        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents)
+        if getattr(self, "_multi_key", None) != key:
+            import numpy as np
+            L = _lib.lib()
+            chunk = L.cris_pack_chunk_elems()
+            assert L.cris_pack_entry_bytes() == 48
+            tab = np.zeros((len(ents), 6), dtype=np.int64)
+            tot = 0
+            for i, (_, (_, m, p)) in enumerate(ents):
+                w = p.detach()
+                if w.dim() == 4 and w.shape[2] == 3 and m.C == 9 * _r8(w.shape[1]):
+                    rows, cols, ld, taps = w.shape[0], w.shape[1], _r8(w.shape[1]), 9
+                else:
+                    rows, cols, ld, taps = w.shape[0], w.numel() // w.shape[0], m.ld, 1
+                tab[i, 0], tab[i, 1], tab[i, 2] = w.data_ptr(), m.buf.data_ptr(), rows
+                tab[i, 3] = cols | (ld << 32)            # int32 cols, int32 ld
+                tab[i, 4] = taps                          # int32 taps, int32 pad
+                tab[i, 5] = tot
+                tot += (rows * taps * ld + chunk - 1) // chunk
+            self._multi_tab = torch.from_numpy(tab).to(ents[0][1][1].buf.device)
+            self._multi_key, self._multi_total = key, tot
+        call("cris_pack_multi", self._multi_tab.data_ptr(), len(ents), self._multi_total)
+        for k, _ in ents:
+            self.done_in_pass.add(k)
+        return True
+
     def get(self, name: str, p: torch.Tensor, as_matrix: bool = False) -> Mat:
         ent = self.cache.get(name)
         key = (p._version, p.data_ptr())
@@ -98,7 +131,7 @@ class PackedWeights:
             buf = ent[1].buf if ent is not None else torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
             call("cris_pack_matrix", w.data_ptr(), buf.data_ptr(), rows, cols, ld)
             m = Mat(buf, rows, cols, ld)
-        self.cache[name] = (key, m)
+        self.cache[name] = (key, m, p)
         return m
 
     def get_folded(self, name: str, p: torch.Tensor, scale_ptr: int, as_matrix: bool = False) -> Mat:
@@ -1150,6 +1183,8 @@ class Run:
     def forward(self):
         if self.training:
             self.e.step_counter(self.dev).add_(7919)
+        if self.e.packed.force and os.environ.get("CRIS_B200_PACK_MULTI", "1") != "0":
+            self.e.packed.refresh_all()  # graph capture: all bf16 weight copies refreshed by one launch
         c3, c4, c5 = self.encode_image()
         wfeat, state = self.encode_text()
         fq = self.fpn(c3, c4, c5, state)

@@ -208,6 +208,13 @@ int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps
  * the reference's OIHW gradient gw[co][ci][t] (autograd of nn.Conv2d, model/clip.py:17-25) */
 int cris_unpack_conv_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int cin_pad, void* stream);
 int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
+/* all weight copies in ONE launch: table_dev = DEVICE array of n_entries records {const float* src; void* dst;
+ * int64 rows; int32 cols; int32 ld; int32 taps; int32 pad; int64 chunk0} (cris_pack_entry_bytes() each): taps == 1 is
+ * cris_pack_matrix(src, dst, rows, cols, ld), taps > 1 is cris_pack_conv_weight(src, dst, rows, cols, taps, ld);
+ * chunk0 = exclusive prefix sum of ceil(rows*taps*ld / cris_pack_chunk_elems()), n_chunks the total */
+int cris_pack_entry_bytes(void);
+int cris_pack_chunk_elems(void);
+int cris_pack_multi(const void* table_dev, int n_entries, long long n_chunks, void* stream);
 /* the same bf16 kernel layouts with every output row (= output channel) multiplied by row_scale[row] first:
  * eval-mode BatchNorm folded into the convolution, w'[co] = w[co] * gamma[co]/sqrt(running_var[co]+eps)
  * (model/layers.py:8-11, model/clip.py:17-25 in model.eval()) */
