@@ -863,7 +863,11 @@ class Run:
             # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
             gw = self.pg(wname)
             gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
-            splits = 0  # the library plans tile width and split-K together (whole waves of its persistent grid)
+            # 0 = the library plans tile width and split-K together (whole waves of its persistent grid; partial sums
+            # meet in fp32 TMA reductions in arrival order).  CRIS_B200_DETERMINISTIC_WGRAD=1: one unit per output
+            # tile (splits = 1) -> every gradient element is written by exactly one reduction into the zeroed buffer,
+            # i.e. bitwise repeatable weight gradients (slower: small layers no longer fill the machine).
+            splits = 1 if os.environ.get("CRIS_B200_DETERMINISTIC_WGRAD", "0") == "1" else 0
             if k == 3:
                 # the nine taps accumulate into a zeroed [cout][9][cin_pad] fp32 scratch with unit column stride (TMA
                 # reductions, csrc/gemm_tc.cu EPI_ACCUM), then one small kernel writes the reference's OIHW layout
@@ -1012,13 +1016,14 @@ class Run:
                     sm = self.col_sum(dy, n_out)
                     self.pg(bname)[r0:r1].copy_(sm[:n_out])
             gw = self.pg(wname)
+            det = 1 if os.environ.get("CRIS_B200_DETERMINISTIC_WGRAD", "0") == "1" else 0
             if transposed_weight:
                 gwm = Mat(gw, n_in, n_out, fp32=True)
-                sp = 0
+                sp = det
                 self.gemm(x, dy, gwm, n_in, n_out, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
             else:
                 gwm = Mat(gw, n_out, n_in, fp32=True, ptr=gw.data_ptr() + 4 * r0 * n_in)
-                sp = 0
+                sp = det
                 self.gemm(dy, x, gwm, n_out, n_in, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
             if x.need_grad:
                 slot, acc = self.grad_slot(x)

@@ -252,6 +252,38 @@ def test_conv_halo_matches_gemm(monkeypatch, N, H, W, cin, cout):
     assert rel(outs["1"][2], xr.grad) < 2e-2
 
 
+def test_deterministic_wgrad_is_bitwise_repeatable(monkeypatch):
+    """CRIS_B200_DETERMINISTIC_WGRAD=1 (splits = 1: each weight-gradient element is produced by exactly one TMA
+    reduction into the zeroed buffer) gives bit-identical conv and linear weight gradients run after run, and the same
+    values as the default split-K plan up to fp32 summation order."""
+    g = torch.Generator().manual_seed(11)
+    N, H, W, cin, cout = 4, 26, 26, 128, 192
+    x = _bf(torch.randn(N, cin, H, W, generator=g))
+    P = {"c.weight": torch.randn(cout, cin, 3, 3, generator=g) * 0.05, "l.weight": torch.randn(96, cin, generator=g) * 0.05,
+         "l.bias": torch.zeros(96)}
+    gz = _bf(torch.randn(N, cout, H, W, generator=g))
+    xt = _bf(torch.randn(3000, cin, generator=g))
+    gy = _bf(torch.randn(3000, 96, generator=g))
+
+    def once():
+        run = _mk_run(P)
+        xm = to_padded(run, x)
+        z, _, _ = run.conv(xm, "c.weight", 3, stats=False)
+        set_grad(run, z, gz)
+        tm = to_mat(run, xt)
+        y = run.linear(tm, "l.weight", "l.bias")
+        set_grad(run, y, gy)
+        backward(run)
+        return run.pgrad["c.weight"].clone(), run.pgrad["l.weight"].clone()
+
+    monkeypatch.setenv("CRIS_B200_DETERMINISTIC_WGRAD", "1")
+    a, b = once(), once()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    monkeypatch.setenv("CRIS_B200_DETERMINISTIC_WGRAD", "0")
+    c = once()
+    assert rel(c[0], a[0]) < 1e-5 and rel(c[1], a[1]) < 1e-5
+
+
 def test_conv_bn_eval_and_bias_conv():
     g = torch.Generator().manual_seed(5)
     N, H, W, cin, cout = 2, 9, 11, 64, 64
