@@ -288,6 +288,47 @@ def latency_extra(arch, model, cfg, pk):
     return res
 
 
+def r101_extra(dev, pk, B=32, steps=5, warmup=3):
+    """cris_r101 train step at the reference config's 32 images per GPU (config/refcoco/cris_r101.yaml batch_size 32 x 8)."""
+    from oracle import synth
+    from cris.pytorch_b200.optim import Adam
+    cfg, model, groups = build_model("r101", dropout=0.1)
+    model = model.to(dev).train()
+    opt = Adam(groups, lr=1e-4, weight_decay=0.0)
+    scaler = torch.amp.GradScaler("cuda")
+    img, word, mask = synth.make_inputs(B, 0, 416, cfg.word_len, synth.ARCHS["r101"]["vocab"])
+    img, word, mask = img.to(dev), word.to(dev), mask.to(dev)
+
+    def step():
+        pred, tgt, loss = model(img, word, mask)
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        model.train_metric()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    v = B / (ms / 1e3)
+    tf = v * F_TRAIN_GF["r101"] / 1e3
+    res = {"images_per_sec": round(v, 1), "ms_per_step": round(ms, 2), "batch": B, "tflops": round(tf, 1),
+           "frac_of_sustained_peak": round(tf / pk["bf16_tflops_sustained"], 4),
+           "workload": "cris_r101 train step (fwd+BCE loss+bwd+Adam+metric), 416x416, word_len 17, batch 32/GPU (BASELINE.json config 4, per GPU)"}
+    model._get_engine().graphs = {}
+    del model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,6 +510,15 @@ def main():
                             "recipe": "tools/latency.py:51-66 of the reference (eval, no_grad, synchronize per call, p50)"}
         except Exception as e:  # noqa: BLE001
             out["extra"] = {"error": repr(e)[:300]}
+    if world == 1 and not args.no_extras and args.arch == "r50":
+        # BASELINE.json config #4 (cris_r101, 32 images per GPU) on this GPU: the same step, 3 warm-up + 5 timed
+        try:
+            engine.graphs, engine.eval_graphs = {}, {}
+            del model, opt
+            torch.cuda.empty_cache()
+            out["extra"]["r101"] = r101_extra(dev, pk)
+        except Exception as e:  # noqa: BLE001
+            out.setdefault("extra", {})["r101"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_incumbent:
         # free this arm's captured graphs first: the incumbent needs its own ~60 GB of eager activations
         engine.graphs, engine.eval_graphs = {}, {}

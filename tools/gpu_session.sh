@@ -75,11 +75,19 @@ except Exception as e: print('   parse error', e)
       timeout 600 python bench.py --steps 10 --warmup 3 --no-incumbent --no-cpu-baseline > gpurun_out/${TAG}_benchq.json 2> gpurun_out/${TAG}_benchq.err
       echo "[benchq] rc=$?"; tail -c 5000 gpurun_out/${TAG}_benchq.json; tail -5 gpurun_out/${TAG}_benchq.err ;;
     ncu_gemm)
+      # captures stay on the box (each --set full report is ~10 MB, gpurun_out may bring back 64 MiB): only the summary returns
+      reps=""
       for i in 3 6 11 13 14 15; do
-        timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -f \
-          -o gpurun_out/${TAG}_gemm_perf$i tests/native/gemm_selftest perf $i > gpurun_out/${TAG}_ncu_gemm$i.log 2>&1
-        echo "[ncu gemm perf $i] rc=$?"
-      done ;;
+        timeout 200 ncu --set full --clock-control none -k regex:gemm_tc -c 1 -f \
+          -o /tmp/${TAG}_gemm_perf$i tests/native/gemm_selftest perf $i > gpurun_out/${TAG}_ncu_gemm$i.log 2>&1
+        echo "[ncu gemm perf $i] rc=$?"; reps="$reps /tmp/${TAG}_gemm_perf$i.ncu-rep"
+      done
+      timeout 200 ncu --set full --clock-control none -k regex:"conv_halo|layernorm_bwd|adam|dynconv_bce_fwd|upsample2x_fwd" -c 6 -f \
+        -o /tmp/${TAG}_misc python tools/profile_step.py 64 > gpurun_out/${TAG}_ncu_misc.log 2>&1
+      echo "[ncu misc] rc=$?"; reps="$reps /tmp/${TAG}_misc.ncu-rep"
+      python tools/ncu_summary.py $reps > gpurun_out/${TAG}_ncu_gemm_summary.md 2>&1
+      cp /tmp/${TAG}_gemm_perf3.ncu-rep gpurun_out/ 2>/dev/null
+      cat gpurun_out/${TAG}_ncu_gemm_summary.md ;;
     ncu_wgrad)
       for i in 11 12 14; do
         timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -f \
