@@ -78,35 +78,48 @@ class PackedWeights:
         self.force = False        # CUDA-graph capture: always (re)launch the pack kernel into the cached buffer
         self.done_in_pass = set()  # ... but only once per captured pass
 
+    def _multi_entries(self):
+        return [(k, v) for k, v in self.cache.items() if not k.endswith("#folded") and len(v) == 3]
+
+    def prepare_multi(self):
+        """Build / refresh the device table of refresh_all() — call OUTSIDE a CUDA-graph capture (it copies host data)."""
+        ents = self._multi_entries()
+        if not ents:
+            self._multi_key = None
+            return
+        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents)
+        if getattr(self, "_multi_key", None) == key:
+            return
+        import numpy as np
+        L = _lib.lib()
+        chunk = L.cris_pack_chunk_elems()
+        assert L.cris_pack_entry_bytes() == 48
+        tab = np.zeros((len(ents), 6), dtype=np.int64)
+        tot = 0
+        for i, (_, (_, m, p)) in enumerate(ents):
+            w = p.detach()
+            if w.dim() == 4 and w.shape[2] == 3 and m.C == 9 * _r8(w.shape[1]):
+                rows, cols, ld, taps = w.shape[0], w.shape[1], _r8(w.shape[1]), 9
+            else:
+                rows, cols, ld, taps = w.shape[0], w.numel() // w.shape[0], m.ld, 1
+            tab[i, 0], tab[i, 1], tab[i, 2] = w.data_ptr(), m.buf.data_ptr(), rows
+            tab[i, 3] = cols | (ld << 32)            # int32 cols, int32 ld
+            tab[i, 4] = taps                          # int32 taps, int32 pad
+            tab[i, 5] = tot
+            tot += (rows * taps * ld + chunk - 1) // chunk
+        self._multi_tab = torch.from_numpy(tab).to(ents[0][1][1].buf.device)
+        self._multi_key, self._multi_total, self._multi_n = key, tot, len(ents)
+
     def refresh_all(self) -> bool:
         """Re-pack EVERY cached copy with one kernel launch (csrc/tokens.cu pack_multi_kernel) and mark them done for
         this pass — used inside CUDA-graph captures, where every copy must be refreshed on every replay (one launch
-        instead of ~143).  The device table is rebuilt only when a source / destination pointer changed."""
-        ents = [(k, v) for k, v in self.cache.items() if not k.endswith("#folded") and len(v) == 3]
-        if not ents:
+        instead of ~143).  Needs prepare_multi() to have run on the current set of copies; otherwise the per-tensor
+        launches of get() take over."""
+        ents = self._multi_entries()
+        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents) if ents else None
+        if not ents or getattr(self, "_multi_key", None) != key:
             return False
-        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents)
-        if getattr(self, "_multi_key", None) != key:
-            import numpy as np
-            L = _lib.lib()
-            chunk = L.cris_pack_chunk_elems()
-            assert L.cris_pack_entry_bytes() == 48
-            tab = np.zeros((len(ents), 6), dtype=np.int64)
-            tot = 0
-            for i, (_, (_, m, p)) in enumerate(ents):
-                w = p.detach()
-                if w.dim() == 4 and w.shape[2] == 3 and m.C == 9 * _r8(w.shape[1]):
-                    rows, cols, ld, taps = w.shape[0], w.shape[1], _r8(w.shape[1]), 9
-                else:
-                    rows, cols, ld, taps = w.shape[0], w.numel() // w.shape[0], m.ld, 1
-                tab[i, 0], tab[i, 1], tab[i, 2] = w.data_ptr(), m.buf.data_ptr(), rows
-                tab[i, 3] = cols | (ld << 32)            # int32 cols, int32 ld
-                tab[i, 4] = taps                          # int32 taps, int32 pad
-                tab[i, 5] = tot
-                tot += (rows * taps * ld + chunk - 1) // chunk
-            self._multi_tab = torch.from_numpy(tab).to(ents[0][1][1].buf.device)
-            self._multi_key, self._multi_total = key, tot
-        call("cris_pack_multi", self._multi_tab.data_ptr(), len(ents), self._multi_total)
+        call("cris_pack_multi", self._multi_tab.data_ptr(), self._multi_n, self._multi_total)
         for k, _ in ents:
             self.done_in_pass.add(k)
         return True
@@ -371,6 +384,7 @@ class GraphedStep:
             for k, b in engine.model.named_buffers():
                 b.copy_(saved[k])
         torch.cuda.synchronize(dev)
+        engine.packed.prepare_multi()  # device table of the one-launch weight repack (host copy: outside the capture)
         engine.packed.force = True
         try:
             with torch.no_grad():
@@ -422,6 +436,7 @@ class GraphedEval:
             del r
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        engine.packed.prepare_multi()
         engine.packed.force = True
         try:
             with torch.no_grad():
