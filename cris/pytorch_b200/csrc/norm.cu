@@ -192,6 +192,32 @@ __global__ void bn_coeffs_kernel(const float* __restrict__ sums, double count, c
   if (invstd_out) invstd_out[c] = inv;
 }
 
+// eval mode, every BatchNorm of the model in ONE launch: table entries {gamma, beta, running_mean, running_var, out, C,
+// c0}; out = [scale | shift | mean | invstd] (4C floats); block -> entry by binary search over the channel prefix c0
+struct BnEvalEntry {
+  const float* gamma; const float* beta; const float* rm; const float* rv;
+  float* out;
+  int C;
+  int c0;  // exclusive prefix sum of ceil(C / 128) blocks
+};
+__global__ void bn_coeffs_multi_kernel(const BnEvalEntry* __restrict__ tab, int n, float eps) {
+  int lo = 0, hi = n - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].c0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const BnEvalEntry e = tab[lo];
+  const int c = (b - e.c0) * 128 + threadIdx.x;
+  if (c >= e.C) return;
+  const float mean = e.rm[c], inv = rsqrtf(e.rv[c] + eps);
+  const float sc = e.gamma[c] * inv;
+  e.out[c] = sc;
+  e.out[e.C + c] = e.beta[c] - mean * sc;
+  e.out[2 * e.C + c] = mean;
+  e.out[3 * e.C + c] = inv;
+}
+
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ resid,
                                 long long ldr, __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int C,
@@ -791,6 +817,14 @@ int cris_bn_finalize_fwd(const float* partials, int n_tiles, int C, float* sums,
 int cris_stats_finalize_bwd(const float* partials, int n_tiles, int C, float* sums, float* g0, float* g1, void* stream) {
   stats_finalize_bwd_kernel<<<(C + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles, C, sums,
                                                                                               g0, g1);
+  CRIS_LAUNCH_OK();
+  return 0;
+}
+int cris_bn_eval_entry_bytes(void) { return (int)sizeof(BnEvalEntry); }
+int cris_bn_coeffs_multi(const void* table_dev, int n_entries, int n_blocks, float eps, void* stream) {
+  CRIS_CHECK_ARG(table_dev != nullptr && n_entries >= 1 && n_blocks >= 1, "cris_bn_coeffs_multi: bad table");
+  bn_coeffs_multi_kernel<<<n_blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const BnEvalEntry*>(table_dev), n_entries, eps);
   CRIS_LAUNCH_OK();
   return 0;
 }

@@ -290,6 +290,7 @@ struct PackEntry {
   int taps;
   int pad_;
   long long chunk0;   // exclusive prefix sum of ceil(dst elements / kPackChunk)
+  const float* row_scale;  // optional per-output-row factor (eval-mode BatchNorm folded into the convolution)
 };
 constexpr int kPackChunk = 8192;
 
@@ -306,14 +307,16 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackEntry* __rest
   for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
     const int c = (int)(i % e.ld);
     float v = 0.f;
+    long long r;
     if (e.taps == 1) {
-      const long long r = i / e.ld;
+      r = i / e.ld;
       if (c < e.cols) v = e.src[r * e.cols + c];
     } else {
       const int t = (int)((i / e.ld) % e.taps);
-      const long long co = i / ((long long)e.ld * e.taps);
-      if (c < e.cols) v = e.src[(co * e.cols + c) * e.taps + t];
+      r = i / ((long long)e.ld * e.taps);
+      if (c < e.cols) v = e.src[(r * e.cols + c) * e.taps + t];
     }
+    if (e.row_scale != nullptr) v *= e.row_scale[r];
     e.dst[i] = f2bf(v);
   }
 }

@@ -79,24 +79,37 @@ class PackedWeights:
         self.done_in_pass = set()  # ... but only once per captured pass
 
     def _multi_entries(self):
-        return [(k, v) for k, v in self.cache.items() if not k.endswith("#folded") and len(v) == 3]
+        """[(cache key, Mat, parameter, scale pointer or 0)]: plain copies, and (eval) BatchNorm-folded copies"""
+        out = []
+        for k, v in self.cache.items():
+            if k.endswith("#folded"):
+                if getattr(self, "_multi_folded", False):
+                    out.append((k, v[0], v[1], v[2]))
+            elif len(v) == 3:
+                out.append((k, v[1], v[2], 0))
+        return out
 
-    def prepare_multi(self):
-        """Build / refresh the device table of refresh_all() — call OUTSIDE a CUDA-graph capture (it copies host data)."""
+    def _multi_sig(self, ents):
+        return tuple((p.data_ptr(), m.buf.data_ptr(), sc) for _, m, p, sc in ents)
+
+    def prepare_multi(self, include_folded: bool = False):
+        """Build / refresh the device table of refresh_all() — call OUTSIDE a CUDA-graph capture (it copies host data).
+        include_folded: the eval graph also refreshes the BatchNorm-folded copies."""
+        self._multi_folded = include_folded
         ents = self._multi_entries()
         if not ents:
             self._multi_key = None
             return
-        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents)
+        key = self._multi_sig(ents)
         if getattr(self, "_multi_key", None) == key:
             return
         import numpy as np
         L = _lib.lib()
         chunk = L.cris_pack_chunk_elems()
-        assert L.cris_pack_entry_bytes() == 48
-        tab = np.zeros((len(ents), 6), dtype=np.int64)
+        assert L.cris_pack_entry_bytes() == 56
+        tab = np.zeros((len(ents), 7), dtype=np.int64)
         tot = 0
-        for i, (_, (_, m, p)) in enumerate(ents):
+        for i, (_, m, p, sc) in enumerate(ents):
             w = p.detach()
             if w.dim() == 4 and w.shape[2] == 3 and m.C == 9 * _r8(w.shape[1]):
                 rows, cols, ld, taps = w.shape[0], w.shape[1], _r8(w.shape[1]), 9
@@ -106,8 +119,9 @@ class PackedWeights:
             tab[i, 3] = cols | (ld << 32)            # int32 cols, int32 ld
             tab[i, 4] = taps                          # int32 taps, int32 pad
             tab[i, 5] = tot
+            tab[i, 6] = sc
             tot += (rows * taps * ld + chunk - 1) // chunk
-        self._multi_tab = torch.from_numpy(tab).to(ents[0][1][1].buf.device)
+        self._multi_tab = torch.from_numpy(tab).to(ents[0][1].buf.device)
         self._multi_key, self._multi_total, self._multi_n = key, tot, len(ents)
 
     def refresh_all(self) -> bool:
@@ -116,12 +130,12 @@ class PackedWeights:
         instead of ~143).  Needs prepare_multi() to have run on the current set of copies; otherwise the per-tensor
         launches of get() take over."""
         ents = self._multi_entries()
-        key = tuple((v[2].data_ptr(), v[1].buf.data_ptr()) for _, v in ents) if ents else None
+        key = self._multi_sig(ents) if ents else None
         if not ents or getattr(self, "_multi_key", None) != key:
             return False
         call("cris_pack_multi", self._multi_tab.data_ptr(), self._multi_n, self._multi_total)
-        for k, _ in ents:
-            self.done_in_pass.add(k)
+        for e in ents:
+            self.done_in_pass.add(e[0])
         return True
 
     def get(self, name: str, p: torch.Tensor, as_matrix: bool = False) -> Mat:
@@ -149,23 +163,26 @@ class PackedWeights:
 
     def get_folded(self, name: str, p: torch.Tensor, scale_ptr: int, as_matrix: bool = False) -> Mat:
         """Eval mode: the same layouts with output channel co scaled by scale[co] (BatchNorm folded into the
-        convolution).  Re-packed on every call: the scale depends on the running statistics, not on p._version."""
+        convolution).  Re-packed on every call (the scale depends on the running statistics, not on p._version) unless
+        refresh_all() already did it for this captured pass."""
         ent = self.cache.get(name + "#folded")
+        if ent is not None and ent[2] == scale_ptr and self.force and (name + "#folded") in self.done_in_pass:
+            return ent[0]
         w = p.detach()
         if w.dim() == 4 and w.shape[2] == 3 and not as_matrix:
             cout, cin = w.shape[0], w.shape[1]
             cp = _r8(cin)
-            buf = ent.buf if ent is not None else torch.empty(cout, 9 * cp, dtype=torch.bfloat16, device=w.device)
+            buf = ent[0].buf if ent is not None else torch.empty(cout, 9 * cp, dtype=torch.bfloat16, device=w.device)
             call("cris_pack_conv_weight_scaled", w.data_ptr(), scale_ptr, buf.data_ptr(), cout, cin, 9, cp)
             m = Mat(buf, cout, 9 * cp)
         else:
             rows = w.shape[0]
             cols = w.numel() // rows
             ld = _r8(cols)
-            buf = ent.buf if ent is not None else torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+            buf = ent[0].buf if ent is not None else torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
             call("cris_pack_matrix_scaled", w.data_ptr(), scale_ptr, buf.data_ptr(), rows, cols, ld)
             m = Mat(buf, rows, cols, ld)
-        self.cache[name + "#folded"] = m
+        self.cache[name + "#folded"] = (m, p, scale_ptr)
         return m
 
 
@@ -232,6 +249,8 @@ class Engine:
         # the GEMM epilogue) instead of a bn_coeffs + bn_apply pass per layer
         self.fold_eval_bn = os.environ.get("CRIS_B200_FOLD_EVAL_BN", "1") != "0"
         self.last_metric_counts: Optional[torch.Tensor] = None  # int32 [B,2] of the last training forward
+        self.eval_coefs: Dict[str, torch.Tensor] = {}  # BN prefix -> persistent [scale|shift|mean|invstd] (eval fold)
+        self._bn_multi = None
         self.graphs: Dict[tuple, "GraphedStep"] = {}
         self.eval_graphs: Dict[tuple, "GraphedEval"] = {}
         self._counter: Optional[torch.Tensor] = None
@@ -256,6 +275,37 @@ class Engine:
             return None
         from . import peer
         return peer.get_exchange(device)
+
+    def eval_coef(self, prefix: str, C: int, device) -> torch.Tensor:
+        t = self.eval_coefs.get(prefix)
+        if t is None or t.device != device or t.numel() != 4 * C:
+            t = torch.empty(4 * C, dtype=torch.float32, device=device)
+            self.eval_coefs[prefix] = t
+        return t
+
+    def prepare_bn_multi(self):
+        """Device table for cris_bn_coeffs_multi over every BatchNorm that eval_coef() has seen (outside captures)."""
+        if not self.eval_coefs:
+            self._bn_multi = None
+            return
+        import numpy as np
+        P, Bf = dict(self.model.named_parameters()), dict(self.model.named_buffers())
+        names = sorted(self.eval_coefs)
+        key = tuple((self.eval_coefs[n].data_ptr(), P[n + ".weight"].data_ptr(), Bf[n + ".running_mean"].data_ptr()) for n in names)
+        if self._bn_multi is not None and self._bn_multi[0] == key:
+            return
+        assert _lib.lib().cris_bn_eval_entry_bytes() == 48
+        tab = np.zeros((len(names), 6), dtype=np.int64)
+        blocks = 0
+        for i, n in enumerate(names):
+            C = P[n + ".weight"].numel()
+            tab[i, 0], tab[i, 1] = P[n + ".weight"].data_ptr(), P[n + ".bias"].data_ptr()
+            tab[i, 2], tab[i, 3] = Bf[n + ".running_mean"].data_ptr(), Bf[n + ".running_var"].data_ptr()
+            tab[i, 4] = self.eval_coefs[n].data_ptr()
+            tab[i, 5] = C | (blocks << 32)
+            blocks += (C + 127) // 128
+        dev = self.eval_coefs[names[0]].device
+        self._bn_multi = (key, torch.from_numpy(tab).to(dev), len(names), blocks, set(names))
 
     def step_counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != device:
@@ -436,7 +486,8 @@ class GraphedEval:
             del r
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        engine.packed.prepare_multi()
+        engine.prepare_bn_multi()
+        engine.packed.prepare_multi(include_folded=True)
         engine.packed.force = True
         try:
             with torch.no_grad():
@@ -932,18 +983,17 @@ class Run:
         cin_pad = _r8(w_cols)
         gamma, beta = self.P[bn_prefix + ".weight"], self.P[bn_prefix + ".bias"]
         rm, rv = self.Bf[bn_prefix + ".running_mean"], self.Bf[bn_prefix + ".running_var"]
-        coef = self.f32(4 * cout)  # scale | shift | mean | invstd
-        call("cris_bn_coeffs", None, 1.0, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(),
-             rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * cout, coef.data_ptr() + 8 * cout,
-             coef.data_ptr() + 12 * cout, cout, 0)
+        coef = self.e.eval_coef(bn_prefix, cout, self.dev)  # scale | shift | mean | invstd, persistent per layer
+        if bn_prefix not in getattr(self, "bn_done", ()):
+            call("cris_bn_coeffs", None, 1.0, gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(),
+                 rv.data_ptr(), coef.data_ptr(), coef.data_ptr() + 4 * cout, coef.data_ptr() + 8 * cout,
+                 coef.data_ptr() + 12 * cout, cout, 0)
         wp = self.e.packed.get_folded(conv_name, Wt, coef.data_ptr())
         y = out if out is not None else self.new(x.rows, cout, False, x.geom)
         act = ACT_NONE if not relu else (ACT_RELU_POST if resid is not None else ACT_RELU)
         self.gemm(x, wp, y, x.rows, cout, cin, bias=coef.data_ptr() + 4 * cout, act=act, resid=resid,
                   mask_geom=x.geom, tap_mode=TAP_ACCUM if k == 3 else TAP_NONE, taps=9 if k == 3 else 1,
                   tap_off=self.taps_of(x.geom) if k == 3 else None, b_tap_k=cin_pad if k == 3 else 0)
-        self._keep = getattr(self, "_keep", [])
-        self._keep.append(coef)  # the bias vector must outlive the launch (eager mode frees on scope exit otherwise)
         return y
 
     # ---- resampling -------------------------------------------------------------------------------
@@ -1203,7 +1253,13 @@ class Run:
     def forward(self):
         if self.training:
             self.e.step_counter(self.dev).add_(7919)
+        self.bn_done = set()
         if self.e.packed.force and os.environ.get("CRIS_B200_PACK_MULTI", "1") != "0":
+            if not self.training and self.e._bn_multi is not None:
+                # eval graph: the coefficients of every folded BatchNorm in one launch, then (below) every weight copy
+                _, tab, n, blocks, names = self.e._bn_multi
+                call("cris_bn_coeffs_multi", tab.data_ptr(), n, blocks, BN_EPS)
+                self.bn_done = names
             self.e.packed.refresh_all()  # graph capture: all bf16 weight copies refreshed by one launch
         c3, c4, c5 = self.encode_image()
         wfeat, state = self.encode_text()

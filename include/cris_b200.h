@@ -133,6 +133,11 @@ int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* su
  * variance) — torch batch_norm_gather_stats_with_counts semantics; under SyncBN the caller all-reduces
  * `sums` across ranks first and passes the global count.  training = 0 uses the running statistics.
  */
+/* eval mode: the coefficients of EVERY BatchNorm in one launch.  table_dev: DEVICE array of records {const float* gamma,
+ * beta, running_mean, running_var; float* out (4C floats: scale|shift|mean|invstd); int32 C; int32 c0} with c0 the
+ * exclusive prefix sum of ceil(C/128); n_blocks = the total (cris_bn_eval_entry_bytes() per record) */
+int cris_bn_eval_entry_bytes(void);
+int cris_bn_coeffs_multi(const void* table_dev, int n_entries, int n_blocks, float eps, void* stream);
 int cris_bn_coeffs(const float* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
                    int C, int training, void* stream);
@@ -209,7 +214,8 @@ int cris_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int taps
 int cris_unpack_conv_wgrad(const float* acc, float* gw, int Cout, int Cin, int taps, int cin_pad, void* stream);
 int cris_pack_matrix(const float* w, void* out, int64_t rows, int cols, int ld, void* stream);
 /* all weight copies in ONE launch: table_dev = DEVICE array of n_entries records {const float* src; void* dst;
- * int64 rows; int32 cols; int32 ld; int32 taps; int32 pad; int64 chunk0} (cris_pack_entry_bytes() each): taps == 1 is
+ * int64 rows; int32 cols; int32 ld; int32 taps; int32 pad; int64 chunk0; const float* row_scale (NULL = none)}
+ * (cris_pack_entry_bytes() each): taps == 1 is
  * cris_pack_matrix(src, dst, rows, cols, ld), taps > 1 is cris_pack_conv_weight(src, dst, rows, cols, taps, ld);
  * chunk0 = exclusive prefix sum of ceil(rows*taps*ld / cris_pack_chunk_elems()), n_chunks the total */
 int cris_pack_entry_bytes(void);
