@@ -462,6 +462,7 @@ class GraphedStep:
                 self.n_fwd, self.n_bwd = n1 - n0, _lib.launch_count() - n1  # kernels inside each graph
                 _lib.lib().cris_add_launch_count(-(self.n_fwd + self.n_bwd) & ((1 << 64) - 1))  # capture != launch
                 self.run = r  # keeps every captured buffer referenced
+                self._tables = getattr(engine.packed, "_multi_tab", None)  # the captured pack launch reads this table
             import gc
             gc.collect()
             gc.freeze()  # the captured pass holds ~10^5 long-lived objects: keep them out of later GC passes
@@ -500,6 +501,8 @@ class GraphedEval:
                 self.n = _lib.launch_count() - n0
                 _lib.lib().cris_add_launch_count(-self.n & ((1 << 64) - 1))  # capture != launch
                 self.pred = r.pred
+                # device tables the captured multi-tensor launches read: keep them alive as long as the graph
+                self._tables = (getattr(engine.packed, "_multi_tab", None), engine._bn_multi)
         finally:
             engine.packed.force = False
 
