@@ -45,6 +45,11 @@ try:
 except Exception as e: print('   parse error', e)
 "
       done; tail -3 gpurun_out/${TAG}_ddp${N}.err ;;
+    ddpq2|ddpq4|ddpq8)
+      N=${part#ddpq}
+      timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 \
+        bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-cpu-baseline --no-incumbent > gpurun_out/${TAG}_ddpq${N}.json 2> gpurun_out/${TAG}_ddpq${N}.err
+      echo "[ddpq$N] rc=$?"; tail -c 1500 gpurun_out/${TAG}_ddpq${N}.json; tail -3 gpurun_out/${TAG}_ddpq${N}.err ;;
     ddpbreak2|ddpbreak4|ddpbreak8)
       N=${part#ddpbreak}
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
