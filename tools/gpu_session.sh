@@ -55,6 +55,9 @@ except Exception as e: print('   parse error', e)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
         tools/ddp_breakdown.py > gpurun_out/${TAG}_ddpbreak${N}.log 2>&1
       echo "[ddpbreak$N] rc=$?"; grep -E "fwd|FAILED" gpurun_out/${TAG}_ddpbreak${N}.log ;;
+    bwdover)
+      timeout 300 python tools/bwd_overhead.py > gpurun_out/${TAG}_bwdover.log 2>&1
+      echo "[bwdover] rc=$?"; tail -3 gpurun_out/${TAG}_bwdover.log ;;
     sweep)
       timeout 900 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_sweep.log 2>&1
       echo "[sweep] rc=$?"; cat gpurun_out/${TAG}_sweep.log | tail -12 ;;
