@@ -458,6 +458,9 @@ class GraphedStep:
                     self.n_bwds.append(_lib.launch_count() - nb0)
                 self.grads = r.collect_grads(names)
                 self.grad_of_name = dict(zip(names, self.grads))
+                P_ = dict(engine.model.named_parameters())
+                self.params = [P_[n] for n in names]
+                self.param_of_name = dict(zip(names, self.params))
                 self.gb = self.gbs[0]
                 self.n_fwd, self.n_bwd = n1 - n0, _lib.launch_count() - n1  # kernels inside each graph
                 _lib.lib().cris_add_launch_count(-(self.n_fwd + self.n_bwd) & ((1 << 64) - 1))  # capture != launch
@@ -468,6 +471,24 @@ class GraphedStep:
             gc.freeze()  # the captured pass holds ~10^5 long-lived objects: keep them out of later GC passes
         finally:
             engine.packed.force = False
+
+
+def _fresh_grads(self, names=None):
+    """Gradients handed to autograd.  AccumulateGrad STEALS a gradient tensor only when nobody else references the
+    tensor object; handing it the static graph buffers themselves (referenced from this object) made it clone every
+    one of the 449 gradients on every step — 2.1 ms of copy kernels after the backward graph (tools/bwd_overhead.py).
+    A fresh alias (`detach()`: new tensor object, same storage) is stolen instead, so `p.grad` IS the graph's buffer.
+    That is only safe while nothing accumulates into an existing `.grad` (the next replay overwrites the buffer), so
+    if any parameter still holds a gradient — gradient accumulation without zero_grad(set_to_none=True) — the
+    copying path is taken."""
+    gl = self.grads if names is None else [self.grad_of_name[n] for n in names]
+    ps = self.params if names is None else [self.param_of_name[n] for n in names]
+    if any(p.grad is not None for p in ps):
+        return [g.clone() for g in gl]
+    return [g.detach() for g in gl]
+
+
+GraphedStep.fresh_grads = _fresh_grads
 
 
 class GraphedEval:
@@ -546,7 +567,7 @@ class _GraphFunction(torch.autograd.Function):
         gs.g.copy_(dloss.detach().float().reshape(1))
         gs.gb.replay()
         _lib.lib().cris_add_launch_count(gs.n_bwd)
-        return (None, None, None, None, *gs.grads)
+        return (None, None, None, None, *gs.fresh_grads())
 
 
 class _GraphFirst(torch.autograd.Function):
@@ -572,7 +593,7 @@ class _GraphFirst(torch.autograd.Function):
         k = len(gs.gbs) - 1
         gs.gbs[k].replay()
         _lib.lib().cris_add_launch_count(gs.n_bwds[k])
-        return (None, None, None, None, *[gs.grad_of_name[n] for n in gs.seg_names[k]])
+        return (None, None, None, None, *gs.fresh_grads(gs.seg_names[k]))
 
 
 class _GraphSeg(torch.autograd.Function):
@@ -593,7 +614,7 @@ class _GraphSeg(torch.autograd.Function):
             gs.g.copy_(dtoken.detach().float().reshape(1))
         gs.gbs[k].replay()
         _lib.lib().cris_add_launch_count(gs.n_bwds[k])
-        return (None, None, dtoken, *[gs.grad_of_name[n] for n in gs.seg_names[k]])
+        return (None, None, dtoken, *gs.fresh_grads(gs.seg_names[k]))
 
 
 class Run:
