@@ -127,7 +127,7 @@ class Adam(torch.optim.Optimizer):
                 if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
                     raise RuntimeError("cris.pytorch_b200.optim.Adam needs dense fp32 CUDA parameters and gradients "
                                        "(no CPU fallback)")
-                st = self.state[p]
+                st = self._state[p]
                 if len(st) == 0:
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
@@ -139,8 +139,8 @@ class Adam(torch.optim.Optimizer):
                 grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in plist]
                 if any(not p.is_contiguous() for p in plist):
                     raise RuntimeError("cris.pytorch_b200.optim.Adam needs contiguous parameters")
-                ms = [self.state[p]["exp_avg"] for p in plist]
-                vs = [self.state[p]["exp_avg_sq"] for p in plist]
+                ms = [self._state[p]["exp_avg"] for p in plist]
+                vs = [self._state[p]["exp_avg_sq"] for p in plist]
                 tab, n, total = self._table(gi * 1024 + si, plist, grads, ms, vs)
                 with torch.cuda.device(plist[0].device):
                     rc = L.cris_adam_step(tab.data_ptr(), n, total, float(group["lr"]), float(group["betas"][0]),
@@ -176,13 +176,30 @@ class Adam(torch.optim.Optimizer):
 
     def _sync_steps(self, gi=None):
         """Bring the per-parameter `step` tensors up to date with the fast path's group counters."""
-        for g, fast in list(self._fast.items()):
+        for g, fast in list(getattr(self, "_fast", {}).items()):
             if gi is not None and g != gi:
                 continue
             if fast["lag"]:
                 for p in self.param_groups[g]["params"]:
-                    self.state[p]["step"] += fast["lag"]
+                    self._state[p]["step"] += fast["lag"]
                 fast["lag"] = 0
+
+    # `optimizer.state[p]["step"]` stays observable exactly like torch.optim.Adam's: any outside access to `.state`
+    # first folds the fast path's pending counts into the per-parameter tensors (step() itself uses `_state`)
+    @property
+    def state(self):
+        self._sync_steps()
+        return self._state
+
+    @state.setter
+    def state(self, value):
+        self._state = value
+
+    def __setstate__(self, state):
+        # torch's Optimizer.__setstate__ / load_state_dict write `state` straight into __dict__, past the property
+        super().__setstate__(state)
+        if "state" in self.__dict__:
+            self._state = self.__dict__.pop("state")
 
     def _resolve_pending(self):
         if self._pending is not None:
