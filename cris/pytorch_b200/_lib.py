@@ -49,6 +49,7 @@ _SIGS = {
     "cris_stats_finalize_bwd": "piipppp",
     "cris_bn_reduce_partials": "piipp",
     "cris_bn_coeffs": "pdppffppppppiip",
+    "cris_bn_bwd_reduce_masked": "pqpqpqppqiiipqpip",
     "cris_bn_apply": "pqpppqpqqiiiip",
     "cris_bn_bwd_apply": "pqpqpqpppppdpqpqiqiiiip",
     "cris_layernorm_fwd": "piqpppqipiqpqppqifp",

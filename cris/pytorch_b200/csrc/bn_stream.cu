@@ -188,7 +188,13 @@ __global__ void __launch_bounds__(BS_THREADS, 2) bn_stream_kernel(const BsArgs p
         }
         st8(p.y + row * p.ldy + c, v);
       } else if (KIND == 1) {
-        if (!in) continue;
+        if (!in) {
+          if (p.dx != nullptr) {  // masked-gradient output: border rows are zero
+            const float zz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            st8(p.dx + row * p.lddx + c, zz);
+          }
+          continue;
+        }
         float a[8];
         ld8s(t0, item, a);
         if (p.mode == 0) {
@@ -210,6 +216,9 @@ __global__ void __launch_bounds__(BS_THREADS, 2) bn_stream_kernel(const BsArgs p
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) { acc0[k] += a[k]; acc1[k] = fmaf(a[k], xv[k] - c0[k], acc1[k]); }
+          // optional: the ReLU-masked gradient dz = dy * (y > 0) leaves with the reduction — it IS the gradient of the
+          // residual branch, and the apply pass then reads it instead of (dy, y): one tensor pass less per layer
+          if (p.dx != nullptr) st8(p.dx + row * p.lddx + c, a);
         }
       } else {
         float o[8], dz[8];
@@ -340,7 +349,8 @@ int bn_apply_stream(const void* x, long long ldx, const float* scale, const floa
 
 int bn_reduce_stream(int mode, const void* a0, long long lda, const void* y, long long ldy, const void* x, long long ldx,
                      const float* mean, const float* invstd, const float* scale, const float* shift, long long rows, int C,
-                     int relu, int hp, int wp, float* partials, int n_part, cudaStream_t s) {
+                     int relu, int hp, int wp, float* partials, int n_part, cudaStream_t s, void* dzm_out = nullptr,
+                     long long lddzm = 0) {
   BsArgs a{};
   a.in[0] = {reinterpret_cast<const __nv_bfloat16*>(a0), lda};
   a.n_in = 1;
@@ -352,6 +362,8 @@ int bn_reduce_stream(int mode, const void* a0, long long lda, const void* y, lon
   }
   a.rows = rows; a.C = C; a.hp = hp; a.wp = wp; a.relu = relu;
   a.mean = mean; a.invstd = invstd; a.scale = scale; a.shift = shift; a.partials = partials;
+  a.dx = reinterpret_cast<__nv_bfloat16*>(dzm_out); a.lddx = lddzm;
+  CRIS_CHECK_ARG(dzm_out == nullptr || (mode == 1 && op_ok(dzm_out, lddzm, C)), "bn_reduce: masked-gradient output misaligned");
   a.n_part = n_part < 1 ? 1 : (n_part > 64 ? 64 : n_part);
   return launch_stream<1>(a, s);
 }

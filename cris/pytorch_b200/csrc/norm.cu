@@ -762,7 +762,8 @@ int bn_apply_stream(const void* x, long long ldx, const float* scale, const floa
                     void* y, long long ldy, long long rows, int C, int relu, int hp, int wp, cudaStream_t s);
 int bn_reduce_stream(int mode, const void* a0, long long lda, const void* y, long long ldy, const void* x, long long ldx,
                      const float* mean, const float* invstd, const float* scale, const float* shift, long long rows, int C,
-                     int relu, int hp, int wp, float* partials, int n_part, cudaStream_t s);
+                     int relu, int hp, int wp, float* partials, int n_part, cudaStream_t s, void* dzm_out = nullptr,
+                     long long lddzm = 0);
 int bn_bwd_apply_stream(const void* dy, long long lddy, const void* y, long long ldy, const void* x, long long ldx,
                         const float* mean, const float* invstd, const float* gamma, const float* beta, const float* sums,
                         double count, void* dx, long long lddx, void* dres, long long lddres, int dres_accumulate,
@@ -797,6 +798,17 @@ int cris_col_reduce(int mode, const void* a, int64_t lda, int a_fp32, const void
   }
   CRIS_LAUNCH_OK();
   return 0;
+}
+
+int cris_bn_bwd_reduce_masked(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
+                              const float* mean, const float* invstd, int64_t rows, int C, int hp, int wp, void* dzm,
+                              int64_t lddzm, float* partials, int n_blocks, void* stream) {
+  CRIS_CHECK_ARG(dy && y && x && mean && invstd && dzm && partials && n_blocks >= 1, "bn_bwd_reduce_masked: null argument");
+  CRIS_CHECK_ARG(bn_stream_ok(rows, C, hp, wp) && al16(dy, lddy) && al16(y, ldy) && al16(x, ldx) && al16(dzm, lddzm),
+                 "bn_bwd_reduce_masked: rows=%lld C=%d outside the streaming kernel's domain (power-of-two C in [8, 2048], "
+                 "rows >= 2048, 16-byte aligned operands): use cris_col_reduce + cris_bn_bwd_apply", (long long)rows, C);
+  return bn_reduce_stream(1, dy, lddy, y, ldy, x, ldx, mean, invstd, nullptr, nullptr, rows, C, 1, hp, wp, partials,
+                          n_blocks < 64 ? n_blocks : 64, reinterpret_cast<cudaStream_t>(stream), dzm, lddzm);
 }
 
 int cris_bn_reduce_partials(const float* partials, int n_tiles, int C, float* sums, void* stream) {

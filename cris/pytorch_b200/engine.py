@@ -881,9 +881,25 @@ class Run:
             part = self.zeros_f32(min(nb, 64) * 2 * C)
             # without a residual the ReLU mask is recomputed from z (x*scale+shift > 0): y is not re-read
             ymask = y if (resid is not None or not relu) else None
-            call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, ymask.ptr if ymask else None, ymask.ld if ymask else 0,
-                 z.ptr, z.ld, 0, coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C, coef.data_ptr(),
-                 coef.data_ptr() + 4 * C, z.rows, C, int(relu), z.hp, z.wp, part.data_ptr(), nb)
+            # residual + ReLU layers (bn3 of every bottleneck): the masked gradient dy*(y>0) is the residual branch's
+            # gradient; the reduction pass writes it there and the apply pass reads it back instead of (dy, y)
+            premasked = None
+            if (relu and resid is not None and resid.need_grad and ymask is not None
+                    and os.environ.get("CRIS_B200_BN_DZM", "1") != "0"):
+                root = resid.root if resid.root is not None else resid
+                stream_ok = (2048 <= z.rows < (1 << 31) and 8 <= C <= 2048 and (C & (C - 1)) == 0
+                             and os.environ.get("CRIS_B200_BN_STREAM", "1") != "0"
+                             and all(m.ptr % 16 == 0 and m.ld % 8 == 0 for m in (dy, ymask, z)))
+                if stream_ok and root.gbuf is None and resid.root is None:
+                    rslot, racc = self.grad_slot(resid)
+                    call("cris_bn_bwd_reduce_masked", dy.ptr, dy.ld, ymask.ptr, ymask.ld, z.ptr, z.ld,
+                         coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C, z.rows, C, z.hp, z.wp, rslot.ptr, rslot.ld,
+                         part.data_ptr(), nb)
+                    premasked = rslot
+            if premasked is None:
+                call("cris_col_reduce", 1, dy.ptr, dy.ld, 0, None, 0, ymask.ptr if ymask else None, ymask.ld if ymask else 0,
+                     z.ptr, z.ld, 0, coef.data_ptr() + 8 * C, coef.data_ptr() + 12 * C, coef.data_ptr(),
+                     coef.data_ptr() + 4 * C, z.rows, C, int(relu), z.hp, z.wp, part.data_ptr(), nb)
             bs = self.f32(2 * C)
             # parameter gradients are LOCAL sums (DDP averages them), dx needs the GLOBAL sums
             gb, gg = self.pg(prefix + ".bias"), self.pg(prefix + ".weight")
@@ -895,6 +911,12 @@ class Run:
                 if self.sync_bn:
                     self.allreduce(bs)
             dz = self.new(z.rows, C, False, z.geom)
+            if premasked is not None:
+                call("cris_bn_bwd_apply", premasked.ptr, premasked.ld, None, 0, z.ptr, z.ld, coef.data_ptr() + 8 * C,
+                     coef.data_ptr() + 12 * C, gamma.data_ptr(), beta.data_ptr(), bs.data_ptr(), count, dz.ptr, dz.ld,
+                     None, 0, 0, z.rows, C, 0, z.hp, z.wp)
+                self.set_grad(z, dz)
+                return
             dres_ptr, dres_ld, dres_acc = None, 0, 0
             if resid is not None and resid.need_grad:
                 slot, acc = self.grad_slot(resid)

@@ -141,6 +141,14 @@ int cris_bn_coeffs_multi(const void* table_dev, int n_entries, int n_blocks, flo
 int cris_bn_coeffs(const float* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
                    float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
                    int C, int training, void* stream);
+/* BatchNorm backward statistics of a layer with residual + ReLU, and the ReLU-masked gradient in the same pass:
+ * dzm = dy * (y > 0) (zero on border rows) is written to `dzm` — it is the gradient of the residual branch — while
+ * (sum dzm, sum dzm*xhat) accumulate into `partials` as cris_col_reduce mode 1 does.  cris_bn_bwd_apply(dzm, y = NULL,
+ * relu = 0, dres = NULL) then finishes the layer without re-reading dy and y.  Streaming kernel only: power-of-two C in
+ * [8, 2048], rows >= 2048, 16-byte aligned operands (anything else is an error; use the two-call path). */
+int cris_bn_bwd_reduce_masked(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* x, int64_t ldx,
+                              const float* mean, const float* invstd, int64_t rows, int C, int hp, int wp, void* dzm,
+                              int64_t lddzm, float* partials, int n_blocks, void* stream);
 /* y = mask(relu?(x*scale[c] + shift[c] (+ resid))) over a padded-NHWC row matrix [rows, C] (bf16) */
 int cris_bn_apply(const void* x, int64_t ldx, const float* scale, const float* shift, const void* resid, int64_t ldr,
                   void* y, int64_t ldy, int64_t rows, int C, int relu, int hp, int wp, void* stream);

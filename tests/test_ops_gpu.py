@@ -185,6 +185,25 @@ def test_bn_stream_kernels_match_register_kernels(monkeypatch, C, N, H, W, relu,
         out[flag] = (y[:, :C].float(), part.reshape(-1, 2 * C).sum(0), part0.reshape(-1, 2 * C).sum(0), dz[:, :C].float(),
                      dres[:, :C].float() if with_y else None, y[:, C:].float())
     a, b = out["0"], out["1"]
+    if with_y and relu:
+        # one-pass-less variant: the reduction also writes the masked gradient, the apply pass reads it back
+        monkeypatch.setenv("CRIS_B200_BN_STREAM", "1")
+        y = torch.empty_like(z)
+        call("cris_bn_apply", z.data_ptr(), ld, scale.data_ptr(), shift.data_ptr(), res_ptr, ld, y.data_ptr(), ld, rows, C, 1, hp, wp)
+        nb = max(1, min(592, rows // 64))
+        part = torch.zeros(min(nb, 64) * 2 * C, device="cuda")
+        dzm = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        call("cris_bn_bwd_reduce_masked", dy.data_ptr(), ld, y.data_ptr(), ld, z.data_ptr(), ld, mean.data_ptr(),
+             invstd.data_ptr(), rows, C, hp, wp, dzm.data_ptr(), ld, part.data_ptr(), nb)
+        sums2 = part.reshape(-1, 2 * C).sum(0).contiguous()
+        dz2 = torch.full((rows, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        call("cris_bn_bwd_apply", dzm.data_ptr(), ld, None, 0, z.data_ptr(), ld, mean.data_ptr(), invstd.data_ptr(),
+             gamma.data_ptr(), beta.data_ptr(), sums2.data_ptr(), float(N * H * W if H else N), dz2.data_ptr(), ld, None, ld, 0,
+             rows, C, 0, hp, wp)
+        torch.cuda.synchronize()
+        assert torch.equal(dzm[:, :C].float(), b[4]) and torch.equal(dzm[:, C:].float(), b[5])
+        assert rel(sums2, b[1]) < 1e-4
+        assert rel(dz2[:, :C].float(), b[3]) < 6e-3
     assert torch.equal(a[0], b[0])                       # forward apply: identical arithmetic
     assert torch.equal(a[5], b[5])                       # columns beyond C (a concat neighbour's slice) untouched
     assert rel(b[1], a[1]) < 1e-4 and rel(b[2], a[2]) < 1e-4
