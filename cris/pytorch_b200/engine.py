@@ -307,6 +307,13 @@ class Engine:
         dev = self.eval_coefs[names[0]].device
         self._bn_multi = (key, torch.from_numpy(tab).to(dev), len(names), blocks, set(names))
 
+    def side_stream(self, device) -> "torch.cuda.Stream":
+        st = getattr(self, "_side", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self._side = st
+        return st
+
     def step_counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != device:
             self._counter = torch.zeros(1, dtype=torch.int64, device=device)
@@ -673,13 +680,18 @@ class Run:
         return torch.empty(n, dtype=torch.float32, device=self.dev)
 
     def zeros_f32(self, n):
-        """n zero floats carved from a shared pre-zeroed arena (one memset per 4M floats instead of one per use)."""
+        """n zero floats carved from a pre-zeroed arena (one memset per 4M floats instead of one per use).  One arena
+        per CUDA stream: the memset is ordered only with the stream it was issued on (the text tower runs on a second
+        stream inside graph captures)."""
         n_al = (n + 63) // 64 * 64
-        if self._zarena is None or self._zoff + n_al > self._zarena.numel():
-            self._zarena = torch.zeros(max(n_al, 1 << 22), dtype=torch.float32, device=self.dev)
-            self._zoff = 0
-        t = self._zarena[self._zoff:self._zoff + n]
-        self._zoff += n_al
+        sid = torch.cuda.current_stream(self.dev).cuda_stream if self.dev.type == "cuda" else 0
+        arenas = self.__dict__.setdefault("_zarenas", {})
+        ar = arenas.get(sid)
+        if ar is None or ar[1] + n_al > ar[0].numel():
+            ar = [torch.zeros(max(n_al, 1 << 22), dtype=torch.float32, device=self.dev), 0]
+            arenas[sid] = ar
+        t = ar[0][ar[1]:ar[1] + n]
+        ar[1] += n_al
         return t
 
     def tap(self, name: str, m: Mat):
@@ -1307,8 +1319,28 @@ class Run:
                 call("cris_bn_coeffs_multi", tab.data_ptr(), n, blocks, BN_EPS)
                 self.bn_done = names
             self.e.packed.refresh_all()  # graph capture: all bf16 weight copies refreshed by one launch
-        c3, c4, c5 = self.encode_image()
-        wfeat, state = self.encode_text()
+        # The text tower (12 blocks on 17 tokens: ~250 latency-bound launches forward + backward) is independent of
+        # the image encoder until the FPN.  Inside a CUDA-graph capture it is issued on a second stream, i.e. as a
+        # parallel branch of the graph: its tiny kernels fill the tails of the image encoder's kernels instead of
+        # adding ~4 ms of mostly idle GPU per step.  (Eager launches keep one stream: host-bound anyway, and the
+        # caching allocator would need cross-stream bookkeeping.)
+        self.text_range = None
+        if (self.dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+                and os.environ.get("CRIS_B200_TEXT_STREAM", "1") != "0"
+                and int(os.environ.get("CRIS_B200_BWD_SEGMENTS", "1")) <= 1):
+            main = torch.cuda.current_stream(self.dev)
+            side = self.e.side_stream(self.dev)
+            side.wait_stream(main)
+            t0 = len(self.tape)
+            with torch.cuda.stream(side):
+                wfeat, state = self.encode_text()
+            self.text_range = (t0, len(self.tape))
+            c3, c4, c5 = self.encode_image()
+            self.image_end = len(self.tape)
+            main.wait_stream(side)
+        else:
+            c3, c4, c5 = self.encode_image()
+            wfeat, state = self.encode_text()
         fq = self.fpn(c3, c4, c5, state)
         fq = self.decoder(fq, wfeat)
         self.projector_and_loss(fq, state)
@@ -1687,10 +1719,29 @@ class Run:
             self.tape = []  # closures <-> Run form reference cycles; drop them so buffers are freed promptly
         n = len(self._rtape)
         i1 = n if i1 is None else min(i1, n)
+        tr = getattr(self, "text_range", None)
+        fork_at = (n - self.image_end) if tr is not None else -1   # reversed position of the image encoder's last closure
+        forked = None
         for i in range(i0, i1):
+            if i == fork_at and torch.cuda.is_current_stream_capturing():
+                # everything the two towers need (FPN / decoder gradients) has been issued: the text tower's backward goes
+                # to the side stream as a parallel branch, the image encoder's backward continues on this one
+                main = torch.cuda.current_stream(self.dev)
+                side = self.e.side_stream(self.dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for j in range(n - tr[1], n - tr[0]):
+                        self.bwd_pos = j
+                        if self._rtape[j] is not None:
+                            self._rtape[j]()
+                            self._rtape[j] = None
+                forked = (main, side)
             self.bwd_pos = i
-            self._rtape[i]()
-            self._rtape[i] = None
+            if self._rtape[i] is not None:
+                self._rtape[i]()
+                self._rtape[i] = None
+        if forked is not None:
+            forked[0].wait_stream(forked[1])
         if i1 >= n:
             self._rtape = []
 
