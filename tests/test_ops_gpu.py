@@ -88,9 +88,8 @@ def _bn_params(g, name, c):
 @pytest.mark.parametrize("k,cin,cout,resid,relu", [(1, 64, 128, False, True), (3, 64, 64, False, True),
                                                    (3, 32, 32, False, True), (1, 128, 256, True, True),
                                                    (3, 130, 64, False, False), (3, 256, 512, False, True)])
-def test_conv_bn_train(k, cin, cout, resid, relu):
+def test_conv_bn_train(k, cin, cout, resid, relu, N=3, H=12, W=10):
     g = torch.Generator().manual_seed(k * 100 + cin)
-    N, H, W = 3, 12, 10
     x = _bf(torch.randn(N, cin, H, W, generator=g))
     w = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
     P, Bf = _bn_params(g, "bn", cout)
@@ -130,6 +129,16 @@ def test_conv_bn_train(k, cin, cout, resid, relu):
     exp_rv = 0.9 * Bf["bn.running_var"] + 0.1 * zz.var((0, 2, 3), unbiased=False) * n / (n - 1)
     assert rel(run.Bf["bn.running_mean"].cpu(), exp_rm) < 1e-2
     assert rel(run.Bf["bn.running_var"].cpu(), exp_rv) < 1e-2
+
+
+@pytest.mark.parametrize("k,cin,cout,resid,relu,N,H,W", [(3, 64, 64, False, True, 8, 52, 52), (1, 256, 64, False, True, 8, 52, 52),
+                                                         (1, 64, 256, True, True, 8, 52, 52), (3, 256, 256, False, True, 16, 26, 26),
+                                                         (3, 32, 64, False, True, 2, 104, 104)])
+def test_conv_bn_train_realistic_shapes(k, cin, cout, resid, relu, N, H, W):
+    """The same forward + dgrad + wgrad + BatchNorm checks at layer-sized problems (23 k - 47 k rows): the halo-tile
+    kernels, split-K wgrad through TMA reductions, the streaming BatchNorm passes (incl. the masked-gradient variant for
+    residual layers) and many persistent tiles per CTA — the regimes the 360-row cases above never reach."""
+    test_conv_bn_train(k, cin, cout, resid, relu, N=N, H=H, W=W)
 
 
 @pytest.mark.parametrize("C,N,H,W,relu,with_y,strided", [(8, 4, 40, 30, True, False, False), (64, 8, 52, 52, True, True, False),
