@@ -9,7 +9,7 @@
 //
 // forward  (one CTA per image x head x 128-query tile, 2 CTAs / SM):
 //   pass 1: S_j = Q K_j^T (tcgen05.mma, fp32 in TMEM) for every 128-key block -> exact row maxima
-//   pass 2: S_j again -> p = exp2(t - max), row sums, dropout (hash of the element index), P_j (bf16) written to
+//   pass 2: S_j again -> p = exp2(t - max), row sums, dropout (row hash x 16-bit hash per column pair, vec.cuh drop_keep_rc), P_j (bf16) written to
 //           shared memory in the canonical 128B-swizzled K-major layout -> O += P_j V_j (tcgen05.mma) ;
 //           epilogue O / (rowsum * (1 - p_drop)) -> bf16, and the row's log2-sum-exp for the backward.
 //   (two passes instead of an online rescale: QK^T is 1/3 of the forward flops and the tensor pipe idles anyway)
