@@ -475,7 +475,8 @@ class GraphedStep:
                 self._tables = getattr(engine.packed, "_multi_tab", None)  # the captured pack launch reads this table
             import gc
             gc.collect()
-            gc.freeze()  # the captured pass holds ~10^5 long-lived objects: keep them out of later GC passes
+            if os.environ.get("CRIS_B200_GC_FREEZE", "1") == "1":  # process-wide side effect: opt-out documented in INTEGRATION.md
+                gc.freeze()  # the captured pass holds ~10^5 long-lived objects: keep them out of later GC passes
         finally:
             engine.packed.force = False
 
