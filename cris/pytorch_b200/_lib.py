@@ -87,6 +87,7 @@ _SIGS = {
     "cris_adam_step": "piqddddddppp",
     "cris_postproc_upsample": "ppiiiiip",
     "cris_postproc_warp_iou": "piiipppfpqp",
+    "cris_feeder_letterbox": "pppiiippppp" "p",
     "cris_attention_fwd": "pqpqpqpqpiiiiffupp",
     "cris_attention_bwd": "pqpqpqpqpq" "pppqpqpq" "iiii" "ffu" "pp",
     "cris_conv3x3_halo": "pqpqipqpiiiiip",
@@ -139,7 +140,7 @@ def exported_symbols():
     return ["cris_last_error", "cris_abi_version", "cris_device_check",
             "cris_launch_count", "cris_add_launch_count", "cris_debug_set_trace", "cris_gemm", "cris_gemm_plan", "cris_gemm_args_size", "cris_gemm_args_last_offset",
             "cris_peer_buffer_bytes", "cris_peer_buffer_create", "cris_peer_buffer_open", "cris_peer_buffer_close",
-            "cris_peer_allreduce_f32", "cris_peer_bn_sync_fwd", "cris_peer_bn_sync_bwd", "cris_postproc_sample_bytes", "cris_pack_entry_bytes", "cris_pack_chunk_elems", "cris_bn_eval_entry_bytes", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]
+            "cris_peer_allreduce_f32", "cris_peer_bn_sync_fwd", "cris_peer_bn_sync_bwd", "cris_postproc_sample_bytes", "cris_feeder_sample_bytes", "cris_pack_entry_bytes", "cris_pack_chunk_elems", "cris_bn_eval_entry_bytes", "cris_adam_table_entry_bytes", "cris_adam_chunk_elems", *_SIGS.keys()]
 
 
 def check(rc: int, what: str):

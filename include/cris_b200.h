@@ -315,6 +315,18 @@ int cris_postproc_upsample(const float* logits, float* prob_up, int B, int H, in
 int cris_postproc_warp_iou(const float* prob_up, int B, int SH, int SW, const void* samples_dev, const uint8_t* gt,
                            uint8_t* pred_out, float thr, unsigned long long* counts, long long max_pixels, void* stream);
 
+/* ---- input transform (SURVEY 8f "next" row 3; utils/dataset.py:148-163,210-221): decoded 8-bit photos -> the model's
+ *      input.  Per sample cv2.warpAffine(photo RGB u8 [h,w,3], m, (OW,OH), INTER_CUBIC, borderValue = border3) with
+ *      OpenCV's 8-bit fixed-point arithmetic (bit-exact), then ((v / 255) - mean) / std in fp32 -> img_out fp32
+ *      [B,3,OH,OW]; optionally cv2.warpAffine(mask u8 [h,w], m, INTER_LINEAR, border 0) / 255 -> mask_out fp32 [B,OH,OW]
+ *      (samples without a mask give zeros).  images / masks: DEVICE byte buffers holding every sample back to back;
+ *      samples_dev: DEVICE array of B records {double m[6]; int h, w; int64 img_off; int64 mask_off (-1 = none)}
+ *      (cris_feeder_sample_bytes() each).  border3 / mean3 / std3 are HOST arrays of three values. */
+int cris_feeder_sample_bytes(void);
+int cris_feeder_letterbox(const uint8_t* images, const uint8_t* masks, const void* samples_dev, int B, int OH, int OW,
+                          const double* border3, const float* mean3, const float* std3, float* img_out, float* mask_out,
+                          void* stream);
+
 /* ---- optimizer step (SURVEY 8f "next" row: torch.optim.Adam driven by GradScaler, train.py:105-111,
  *      engine/engine.py:52-57).  One launch updates every tensor of a parameter group:
  *      g' = g / *grad_scale (+ weight_decay * p); m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).

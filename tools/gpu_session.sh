@@ -72,6 +72,10 @@ except Exception as e: print('   parse error', e)
       timeout 300 python -m pytest tests/test_postproc_gpu.py tests/test_ops_gpu.py -k "postproc or bn_stream or conv_bn" -q --no-header -p no:cacheprovider -rA \
         > gpurun_out/${TAG}_tests_post.log 2>&1
       echo "[tests_post] rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|assert" gpurun_out/${TAG}_tests_post.log | tail -20 ;;
+    tests_feeder)
+      timeout 400 python -m pytest tests/test_feeder_gpu.py tests/test_ops_gpu.py -k "feeder or letterbox or realistic" -q --no-header -p no:cacheprovider -rA \
+        > gpurun_out/${TAG}_tests_feeder.log 2>&1
+      echo "[tests_feeder] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error" gpurun_out/${TAG}_tests_feeder.log | tail -30 ;;
     tests_optim)
       timeout 300 python -m pytest tests/test_optim_gpu.py tests/test_syncbn_equiv_gpu.py -q --no-header -p no:cacheprovider -rA > gpurun_out/${TAG}_tests_optim.log 2>&1
       echo "[tests_optim] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_tests_optim.log | tail -8 ;;
