@@ -314,6 +314,14 @@ class Engine:
             self._side = st
         return st
 
+    def wgrad_stream(self, device) -> "torch.cuda.Stream":
+        """Lowest-priority stream for the weight-gradient branch of the captured backward (Run.leaf_branch)."""
+        st = getattr(self, "_wgrad_side", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device, priority=0)
+            self._wgrad_side = st
+        return st
+
     def step_counter(self, device) -> torch.Tensor:
         if self._counter is None or self._counter.device != device:
             self._counter = torch.zeros(1, dtype=torch.int64, device=device)
@@ -459,7 +467,11 @@ class GraphedStep:
                 for k in range(len(self.seg_names)):
                     gb = torch.cuda.CUDAGraph()
                     nb0 = _lib.launch_count()
-                    with torch.cuda.graph(gb, pool=self.gf.pool()):
+                    # the dependent chain is captured on a high-priority stream: where the weight-gradient branch
+                    # (Run.leaf_branch, default-priority stream) competes for SMs, the chain's thread blocks go first
+                    cap = (torch.cuda.Stream(device=dev, priority=-1)
+                           if os.environ.get("CRIS_B200_WGRAD_STREAM", "1") == "1" else None)
+                    with torch.cuda.graph(gb, pool=self.gf.pool(), **({"stream": cap} if cap is not None else {})):
                         r.backward_range(self.g, self.bounds[k], self.bounds[k + 1] if k + 1 < len(self.seg_names) else None)
                     self.gbs.append(gb)
                     self.n_bwds.append(_lib.launch_count() - nb0)
@@ -714,18 +726,52 @@ class Run:
         g = self.pgrad.get(name)
         if g is None:
             if not self.pgrad:
-                total, offs = 0, {}
-                for k, p in self.P.items():
-                    offs[k] = total
-                    total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
-                flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
-                for k, p in self.P.items():
-                    self.pgrad[k] = flat[offs[k]:offs[k] + p.numel()].view(p.shape)
+                self.ensure_pgrad()
                 g = self.pgrad.get(name)
             if g is None:
                 g = torch.zeros_like(self.P[name], dtype=torch.float32)
                 self.pgrad[name] = g
         return g
+
+    def ensure_pgrad(self):
+        """Allocate + zero the flat gradient buffer on the CURRENT stream (called before any branch forks)."""
+        if self.pgrad:
+            return
+        total, offs = 0, {}
+        for k, p in self.P.items():
+            offs[k] = total
+            total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for k, p in self.P.items():
+            self.pgrad[k] = flat[offs[k]:offs[k] + p.numel()].view(p.shape)
+
+    def leaf_branch(self, fn, hold=()):
+        """Run a LEAF of the backward (a weight / bias gradient: nothing downstream in this pass reads its result) as a
+        parallel branch of the captured graph: issued on a second, lower-priority stream forked from the current one, so
+        its persistent kernels fill the launch gaps and tails of the dependent chain (dgrad -> BatchNorm backward ->
+        dgrad ...) instead of sitting in it.  `hold` are the tensors the leaf reads: they stay referenced until the
+        branch is joined (join_leaves), because the chain could otherwise free and re-use their memory while the leaf
+        still runs.  Eager (non-captured) execution and the text-tower branch run the leaf in line."""
+        st = getattr(self, "_leaf_main", None)
+        if (st is None or self.dev.type != "cuda" or not torch.cuda.is_current_stream_capturing()
+                or torch.cuda.current_stream(self.dev) != st):
+            fn()
+            return
+        ws = self.e.wgrad_stream(self.dev)
+        ws.wait_stream(st)
+        with torch.cuda.stream(ws):
+            fn()
+        self._leaf_hold.extend(hold)
+        self._leaf_pending += 1
+        if self._leaf_pending >= self._leaf_join_every:
+            self.join_leaves()
+
+    def join_leaves(self):
+        if getattr(self, "_leaf_pending", 0):
+            self._leaf_main.wait_stream(self.e.wgrad_stream(self.dev))
+            self._leaf_pending = 0
+        if getattr(self, "_leaf_hold", None):
+            self._leaf_hold.clear()
 
     def on_backward(self, fn):
         if self.record:
@@ -983,25 +1029,29 @@ class Run:
             dz = self.grad_of(z)
             if dz is None:
                 return
-            if bias_name:
-                self.pg(bias_name).copy_(self.col_sum(dz, cout, z.hp, z.wp)[:cout])
-            # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
-            gw = self.pg(wname)
-            gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
-            # 0 = the library plans tile width and split-K together (whole waves of its persistent grid; partial sums
-            # meet in fp32 TMA reductions in arrival order).  CRIS_B200_DETERMINISTIC_WGRAD=1: one unit per output
-            # tile (splits = 1) -> every gradient element is written by exactly one reduction into the zeroed buffer,
-            # i.e. bitwise repeatable weight gradients (slower: small layers no longer fill the machine).
-            splits = 1 if os.environ.get("CRIS_B200_DETERMINISTIC_WGRAD", "0") == "1" else 0
-            if k == 3:
-                # the nine taps accumulate into a zeroed [cout][9][cin_pad] fp32 scratch with unit column stride (TMA
-                # reductions, csrc/gemm_tc.cu EPI_ACCUM), then one small kernel writes the reference's OIHW layout
-                acc = Mat(self.zeros_f32(cout * 9 * cin_pad), cout, 9 * cin_pad, fp32=True)
-                self.gemm(dz, x, acc, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
-                          d_tap_n=cin_pad, splits=splits, accumulate=1)
-                call("cris_unpack_conv_wgrad", acc.ptr, gw.data_ptr(), cout, w_cols, 9, cin_pad)
-            else:
-                self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, splits=splits, accumulate=1)
+            def wgrad():
+                if bias_name:
+                    self.pg(bias_name).copy_(self.col_sum(dz, cout, z.hp, z.wp)[:cout])
+                # wgrad: dW[co][ci][tap] += sum_rows dz[row][co] * x[row + off_tap][ci]   (fp32, split-K atomics)
+                gw = self.pg(wname)
+                gwm = Mat(gw, cout, w_cols * (9 if k == 3 else 1), fp32=True)
+                # 0 = the library plans tile width and split-K together (whole waves of its persistent grid; partial
+                # sums meet in fp32 TMA reductions in arrival order).  CRIS_B200_DETERMINISTIC_WGRAD=1: one unit per
+                # output tile (splits = 1) -> every gradient element is written by exactly one reduction into the
+                # zeroed buffer, i.e. bitwise repeatable weight gradients (slower: small layers no longer fill the
+                # machine).
+                splits = 1 if os.environ.get("CRIS_B200_DETERMINISTIC_WGRAD", "0") == "1" else 0
+                if k == 3:
+                    # the nine taps accumulate into a zeroed [cout][9][cin_pad] fp32 scratch with unit column stride
+                    # (TMA reductions, csrc/gemm_tc.cu EPI_ACCUM), then one small kernel writes the reference's OIHW
+                    acc = Mat(self.zeros_f32(cout * 9 * cin_pad), cout, 9 * cin_pad, fp32=True)
+                    self.gemm(dz, x, acc, cout, cin, x.rows, a_mn=1, b_mn=1, tap_mode=TAP_WGRAD, taps=9, tap_off=offs,
+                              d_tap_n=cin_pad, splits=splits, accumulate=1)
+                    call("cris_unpack_conv_wgrad", acc.ptr, gw.data_ptr(), cout, w_cols, 9, cin_pad)
+                else:
+                    self.gemm(dz, x, gwm, cout, cin, x.rows, a_mn=1, b_mn=1, splits=splits, accumulate=1)
+
+            self.leaf_branch(wgrad, (dz, x, z))
             # dgrad: dx[row] = sum_tap dz[row - off_tap] * W_tap
             if x.need_grad:
                 slot, acc = self.grad_slot(x)
@@ -1126,6 +1176,25 @@ class Run:
                 t = self.new(y.rows, y.C, False, None, ld=wpad)
                 self.ew(0, Mat(dy.buf, dy.rows, wpad, dy.ld, True, ptr=dy.ptr), None, Mat(t.buf, t.rows, wpad, wpad))
                 dy = t
+            dy_ = dy
+
+            def wgrad(dy=dy_):
+                self._linear_wgrad(dy, x, wname, bname, r0, r1, n_in, n_out, transposed_weight)
+
+            self.leaf_branch(wgrad, (dy_, x, y))
+            if x.need_grad:
+                slot, acc = self.grad_slot(x)
+                if slot.fp32:
+                    raise RuntimeError("linear input gradients are bf16")
+                self.gemm(dy, wv, slot, x.rows, n_in, n_out, b_mn=0 if transposed_weight else 1,
+                          resid=slot if acc else None, b_rows=0 if transposed_weight else n_out)
+
+        if self.training:
+            self.on_backward(bwd)
+        return (y, part, n_tiles) if stats else y
+
+    def _linear_wgrad(self, dy, x, wname, bname, r0, r1, n_in, n_out, transposed_weight):
+        if True:
             if bname:
                 if os.environ.get("CRIS_B200_BIAS_MMA", "1") == "1" and dy.rows >= 1024 and n_out % 8 == 0:
                     # bias gradient on the tensor cores: 1^T . dy as an M = 1 GEMM (the ones vector is the only
@@ -1149,16 +1218,6 @@ class Run:
                 gwm = Mat(gw, n_out, n_in, fp32=True, ptr=gw.data_ptr() + 4 * r0 * n_in)
                 sp = det
                 self.gemm(dy, x, gwm, n_out, n_in, x.rows, a_mn=1, b_mn=1, splits=sp, accumulate=1)
-            if x.need_grad:
-                slot, acc = self.grad_slot(x)
-                if slot.fp32:
-                    raise RuntimeError("linear input gradients are bf16")
-                self.gemm(dy, wv, slot, x.rows, n_in, n_out, b_mn=0 if transposed_weight else 1,
-                          resid=slot if acc else None, b_rows=0 if transposed_weight else n_out)
-
-        if self.training:
-            self.on_backward(bwd)
-        return (y, part, n_tiles) if stats else y
 
     def layernorm(self, x: Mat, prefix: str, add: Optional[torch.Tensor] = None, want_y=True, want_y2=False):
         """y = LN(x) (bf16); y2 = y + add[row % period] (bf16) — nn.LayerNorm (+ with_pos_embed,
@@ -1707,6 +1766,12 @@ class Run:
         The whole backward is backward_range(dloss, 0, None); GraphedStep may capture it in several ranges so that
         gradients of the late layers reach DistributedDataParallel while the early layers are still running."""
         self.in_backward = True
+        self.ensure_pgrad()
+        self._leaf_main, self._leaf_hold, self._leaf_pending = None, [], 0
+        self._leaf_join_every = max(1, int(os.environ.get("CRIS_B200_WGRAD_JOIN", "64")))
+        if (self.dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+                and os.environ.get("CRIS_B200_WGRAD_STREAM", "1") == "1"):
+            self._leaf_main = torch.cuda.current_stream(self.dev)
         if i0 == 0:
             xf, t, B, Ho, Wo, C = self._head
             g = dloss.detach().float().reshape(1).contiguous()
@@ -1741,6 +1806,8 @@ class Run:
             if self._rtape[i] is not None:
                 self._rtape[i]()
                 self._rtape[i] = None
+        self.join_leaves()
+        self._leaf_main = None
         if forked is not None:
             forked[0].wait_stream(forked[1])
         if i1 >= n:

@@ -180,8 +180,9 @@ def test_training_reduces_loss_and_state_dict_roundtrip(tiny):
 
 def test_segmented_backward_graphs_give_the_same_gradients(tiny, monkeypatch):
     """CRIS_B200_BWD_SEGMENTS=3 captures the backward as three graphs chained through autograd (gradients of the
-    late layers are handed to DDP before the early layers run): same kernels, same gradients (fp32 atomics in the
-    split-K / statistics paths make the comparison 1e-4-close instead of bitwise)."""
+    late layers are handed to DDP before the early layers run): same kernels, same gradients.  Not bitwise: fp32 atomics in
+    the split-K / statistics paths differ in arrival order between two executions, and a 1e-7 difference upstream flips
+    bf16 roundings downstream — observed up to 4e-3 on single tensors between two runs of the SAME setting; bound 3e-2."""
     cfg, sd, model = tiny
     eng = model._get_engine()
     img, word, mask = synth.make_inputs(2, 5, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
@@ -210,7 +211,47 @@ def test_segmented_backward_graphs_give_the_same_gradients(tiny, monkeypatch):
     assert abs(grads["1"][0] - grads["3"][0]) < 1e-6
     assert grads["1"][1].keys() == grads["3"][1].keys() and len(grads["1"][1]) > 100
     for k, g1 in grads["1"][1].items():
-        assert rel(grads["3"][1][k], g1) < 1e-3, k
+        assert rel(grads["3"][1][k], g1) < 3e-2, k
+
+
+def test_weight_gradient_branch_gives_the_same_gradients(tiny, monkeypatch):
+    """CRIS_B200_WGRAD_STREAM=1 issues every weight / bias gradient of the image path on a second stream inside the
+    captured backward (engine.Run.leaf_branch): a scheduling change only — same kernels, same inputs — so the gradients
+    must agree to the run-to-run level of the fp32 atomics (see the segmented-backward test above), also with a join after
+    every leaf and with the graph replayed twice."""
+    cfg, sd, model = tiny
+    eng = model._get_engine()
+    img, word, mask = synth.make_inputs(2, 5, 128, cfg.word_len, synth.ARCHS["tiny"]["vocab"])
+    img, word, mask = img.cuda(), word.cuda(), mask.cuda()
+    model.train()
+    saved = {k: b.clone() for k, b in model.named_buffers()}
+    grads = {}
+    for tag, env in (("off", {"CRIS_B200_WGRAD_STREAM": "0"}), ("on", {"CRIS_B200_WGRAD_STREAM": "1"}),
+                     ("join1", {"CRIS_B200_WGRAD_STREAM": "1", "CRIS_B200_WGRAD_JOIN": "1"})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        eng.graphs = {}
+        for rep in range(2):   # second iteration = a pure replay of the captured graphs
+            with torch.no_grad():
+                for k, b in model.named_buffers():
+                    b.copy_(saved[k])
+            model.zero_grad()
+            pred, m, loss = model(img, word, mask)
+            (loss * 3.0).backward()
+        torch.cuda.synchronize()
+        grads[tag] = (float(loss), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+        monkeypatch.delenv("CRIS_B200_WGRAD_JOIN", raising=False)
+    monkeypatch.delenv("CRIS_B200_WGRAD_STREAM", raising=False)
+    eng.graphs = {}
+    with torch.no_grad():
+        for k, b in model.named_buffers():
+            b.copy_(saved[k])
+    model.eval()
+    for tag in ("on", "join1"):
+        assert abs(grads["off"][0] - grads[tag][0]) < 1e-6
+        assert grads["off"][1].keys() == grads[tag][1].keys() and len(grads[tag][1]) > 100
+        for k, g1 in grads["off"][1].items():
+            assert rel(grads[tag][1][k], g1) < 3e-2, (tag, k)
 
 
 def test_dropout_path_runs(tiny):

@@ -76,6 +76,13 @@ except Exception as e: print('   parse error', e)
       timeout 400 python -m pytest tests/test_feeder_gpu.py tests/test_ops_gpu.py -k "feeder or letterbox or realistic" -q --no-header -p no:cacheprovider -rA \
         > gpurun_out/${TAG}_tests_feeder.log 2>&1
       echo "[tests_feeder] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error" gpurun_out/${TAG}_tests_feeder.log | tail -30 ;;
+    wgstream)
+      timeout 300 python -m pytest tests/test_parity_gpu.py -k "weight_gradient_branch or segmented" -q --no-header -p no:cacheprovider -rA \
+        > gpurun_out/${TAG}_tests_wgstream.log 2>&1
+      echo "[tests_wgstream] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed|assert|Error" gpurun_out/${TAG}_tests_wgstream.log | tail -12
+      CRIS_SWEEP="CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=1000,CRIS_B200_WGRAD_STREAM=0,CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=64,CRIS_B200_WGRAD_STREAM=0+CRIS_X=1,CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=1000+CRIS_X=1" \
+        timeout 600 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_wgstream_sweep.log 2>&1
+      echo "[wgstream sweep] rc=$?"; cat gpurun_out/${TAG}_wgstream_sweep.log | tail -8 ;;
     tests_optim)
       timeout 300 python -m pytest tests/test_optim_gpu.py tests/test_syncbn_equiv_gpu.py -q --no-header -p no:cacheprovider -rA > gpurun_out/${TAG}_tests_optim.log 2>&1
       echo "[tests_optim] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_tests_optim.log | tail -8 ;;
