@@ -470,7 +470,8 @@ class GraphedStep:
                     # the dependent chain is captured on a high-priority stream: where the weight-gradient branch
                     # (Run.leaf_branch, default-priority stream) competes for SMs, the chain's thread blocks go first
                     cap = (torch.cuda.Stream(device=dev, priority=-1)
-                           if os.environ.get("CRIS_B200_WGRAD_STREAM", "1") == "1" else None)
+                           if (os.environ.get("CRIS_B200_WGRAD_STREAM", "1") == "1"
+                               and os.environ.get("CRIS_B200_WGRAD_PRIO", "1") == "1") else None)
                     with torch.cuda.graph(gb, pool=self.gf.pool(), **({"stream": cap} if cap is not None else {})):
                         r.backward_range(self.g, self.bounds[k], self.bounds[k + 1] if k + 1 < len(self.seg_names) else None)
                     self.gbs.append(gb)
@@ -1795,13 +1796,19 @@ class Run:
                 main = torch.cuda.current_stream(self.dev)
                 side = self.e.side_stream(self.dev)
                 side.wait_stream(main)
+                # The branch reads gradients that were ALLOCATED on this stream (word features, sentence state).  The
+                # caching allocator would hand their memory back to this stream the moment the branch's closures drop
+                # them — while the branch is still a concurrent part of the graph — so the closures (and through them
+                # every tensor the branch touches) stay referenced until the join below.
+                branch_refs = []
                 with torch.cuda.stream(side):
                     for j in range(n - tr[1], n - tr[0]):
                         self.bwd_pos = j
                         if self._rtape[j] is not None:
                             self._rtape[j]()
+                            branch_refs.append(self._rtape[j])
                             self._rtape[j] = None
-                forked = (main, side)
+                forked = (main, side, branch_refs)
             self.bwd_pos = i
             if self._rtape[i] is not None:
                 self._rtape[i]()
@@ -1810,6 +1817,7 @@ class Run:
         self._leaf_main = None
         if forked is not None:
             forked[0].wait_stream(forked[1])
+            forked[2].clear()
         if i1 >= n:
             self._rtape = []
 
