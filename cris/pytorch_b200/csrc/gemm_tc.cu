@@ -80,7 +80,11 @@ enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_RESID = 2, EPI_ACCUM = 3 };
 // inside the chunk loop costs a constant-bank load -> uniform predicate -> branch chain (~50-100 cycles each with
 // only two warps per scheduler to hide it; ncu: stall_short_sb on UISETP after LDCU)
 enum { F_BIAS = 1, F_RELU = 2, F_FAST = 4, F_TMA = 8, F_DFP32 = 16, F_STATS = 32, F_WGRAD = 64, F_ALPHA = 128,
-       F_RELU_POST = 256 /* ReLU after the residual add: relu(acc + bias + resid), folded eval-mode BatchNorm */ };
+       F_RELU_POST = 256 /* ReLU after the residual add: relu(acc + bias + resid), folded eval-mode BatchNorm */,
+       F_WG3 = 512 /* 3x3 wgrad with <= 64 input channels: one unit = the three taps of one kernel ROW (dx = -1, 0, +1).
+                      They read the same x rows shifted by one, so ONE (BK + 2)-row box serves all three (descriptor start
+                      shifted by one 128-byte row per tap) and the dz tile is loaded once instead of three times: the L2
+                      traffic of these L2-bound layers drops from 18 to ~6 operand passes.  Three 64-column accumulators. */ };
 
 struct ChunkCtx {
   long long drow, rrow;  // element offsets of this lane's row in D / resid (batch offsets included)
@@ -348,6 +352,23 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKArgs& p, int tile, i
   return t;
 }
 
+// F_WG3 stage layout (instance <256, 64, MN, MN, ACCUM> only): the generic 48 KB stage would hold 4 stages of which 24 KB
+// are used — too little data in flight per SM (measured: 0.49 ms where the traffic allows ~0.2).  WG3 re-partitions the
+// same shared memory: [A: 64 k-rows x 128 B per 64-row M block][B: 66 rows x 128 B, padded to 9 KB].  M <= 64 (all
+// small-channel layers): one A block per stage, 10 stages, and the never-loaded upper M block of the M = 128 MMA is ONE
+// zeroed 8 KB block behind the stages that every stage's descriptor reaches through its LBO.  M > 64: 2 blocks, 7 stages.
+struct Wg3Layout {
+  int stages, stage_bytes, a_blocks;
+  uint32_t zero_off;  // byte offset of the shared zero block (a_blocks == 1)
+};
+__device__ __forceinline__ Wg3Layout wg3_layout(int M) {
+  Wg3Layout l;
+  if (M <= 64) { l.stages = 10; l.stage_bytes = 8192 + 9216; l.a_blocks = 1; l.zero_off = 10 * (8192 + 9216); }
+  else { l.stages = 7; l.stage_bytes = 16384 + 9216; l.a_blocks = 2; l.zero_off = 0; }
+  return l;
+}
+constexpr int WG3_MAX_STAGES = 10;
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (n fastest, so CTAs running
 // together share A rows in L2).  The smem ring keeps rolling across tiles; the TMEM accumulator is double
 // buffered so the epilogue of tile j overlaps the MMAs of tile j+1.
@@ -376,8 +397,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  constexpr bool kWg3Inst = (BN == 256 && A_MN && B_MN && EPI == EPI_ACCUM);
+  if constexpr (kWg3Inst) {
+    static_assert(STAGES <= WG3_MAX_STAGES && (2 * WG3_MAX_STAGES + 4) * 8 + 4 <= 512, "barrier area");
+    if (p.flags & F_WG3) {  // up to 10 stages: the barrier arrays are re-laid out inside the same 512-byte area
+      empty_bar = full_bar + WG3_MAX_STAGES;
+      tmem_full = empty_bar + WG3_MAX_STAGES;
+      tmem_empty = tmem_full + 2;
+      tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    }
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    const int nbar = (kWg3Inst && (p.flags & F_WG3)) ? WG3_MAX_STAGES : STAGES;
+    for (int s = 0; s < nbar; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
@@ -393,6 +425,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (p.tma_store) ptx::prefetch_tmap(&tmD);
   }
   if (warp == EPI_WARPS + 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if constexpr (kWg3Inst) {
+    if ((p.flags & F_WG3) && p.M <= 64) {  // the shared zero block: rows 64..127 of every stage's M = 128 A tile
+      uint4* z = reinterpret_cast<uint4*>(smem + wg3_layout(p.M).zero_off);
+      for (int i = threadIdx.x; i < BK * 128 / 16; i += GEMM_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      ptx::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -405,14 +444,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile, tiles_n, tiles_m, BN);
         for (int i = 0; i < tc.total_iters; ++i, ++it) {
+          if constexpr (kWg3Inst) {
+            if (p.flags & F_WG3) {
+              const Wg3Layout wl = wg3_layout(p.M);
+              const int s3 = it % wl.stages;
+              const uint32_t ph3 = (uint32_t)(it / wl.stages) & 1u;
+              const int k3 = (tc.kb_begin + i) * BK;
+              ptx::mbar_wait(&empty_bar[s3], ph3 ^ 1u, 100 + s3);
+              uint8_t* sa3 = smem + s3 * wl.stage_bytes;
+              ptx::mbar_arrive_expect_tx(&full_bar[s3], wl.a_blocks * (BK * 128) + (BK + 2) * 128);
+              for (int q = 0; q < wl.a_blocks; ++q)
+                ptx::tma_load_4d(sa3 + q * (BK * 128), &tmA, &full_bar[s3], tc.m0 + 64 * q, k3, tc.b_in, tc.b_out);
+              // rows k + off(dy, dx = -1) .. + BK + 1 of x: the window of the three taps of kernel row `ztap`
+              ptx::tma_load_4d(sa3 + wl.a_blocks * (BK * 128), &tmB, &full_bar[s3], 0, k3 + p.tap_off[3 * tc.ztap],
+                               tc.b_in, tc.b_out);
+              continue;
+            }
+          }
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           const int t = (p.tap_mode == CRIS_TAP_ACCUM) ? (i / tc.kb_cnt) : tc.ztap;
           const int k = (tc.kb_begin + (i % tc.kb_cnt)) * BK;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
-          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           const int a_row_off = (p.tap_mode == CRIS_TAP_ACCUM) ? p.tap_off[t] : 0;
           int b_k_off = 0, b_n_off = 0;
           if (p.tap_mode == CRIS_TAP_ACCUM) {
@@ -454,6 +510,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         ptx::tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
         for (int i = 0; i < tc.total_iters; ++i, ++it) {
+          if constexpr (kWg3Inst) {
+            if (p.flags & F_WG3) {
+              const Wg3Layout wl = wg3_layout(p.M);
+              const int s3 = it % wl.stages;
+              const uint32_t ph3 = (uint32_t)(it / wl.stages) & 1u;
+              ptx::mbar_wait(&full_bar[s3], ph3, 200 + s3);
+              ptx::tc_fence_after();
+              const uint32_t sa3 = ptx::smem_u32(smem + s3 * wl.stage_bytes);
+              const uint32_t sb3 = sa3 + wl.a_blocks * (BK * 128);
+              // second M block: the next 8 KB of the stage, or the shared zero block (its LBO differs per stage)
+              const uint32_t lbo = wl.a_blocks == 2 ? (uint32_t)(BK * 128) : ptx::smem_u32(smem + wl.zero_off) - sa3;
+              const uint64_t adesc3 = ptx::make_smem_desc(sa3, lbo, 1024, ptx::kLayoutSW128);
+              // ONE N = 192 MMA per 16 k-rows covers the three taps: an MN-major B operand is made of 64-column blocks
+              // LBO bytes apart, and LBO = 128 B = one x row, so block j is the window shifted by j rows (dx = j - 1).
+              // dz (A) is read from shared memory once instead of three times; accumulator columns 64 j .. 64 j + 63 = tap j.
+              const uint64_t bdesc3 = ptx::make_smem_desc(sb3, 128, 1024, ptx::kLayoutSW128);
+              constexpr uint32_t idesc3 = ptx::make_idesc_bf16(BM, 192, 1, 1);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)
+                ptx::umma_bf16(tacc, adesc3 + (uint64_t)((kk * 2048) >> 4), bdesc3 + (uint64_t)((kk * 2048) >> 4), idesc3,
+                               (i > 0 || kk > 0) ? 1u : 0u);
+              ptx::umma_commit(&empty_bar[s3]);
+              continue;
+            }
+          }
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           ptx::mbar_wait(&full_bar[s], ph, 200 + s);
@@ -534,6 +615,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       CRIS_TRACE(acc, 0);
 #pragma unroll 1
       for (int c = chalf; c < NCHUNK; c += 2) {
+        bool wg3 = false;
+        if constexpr (BN == 256 && A_MN && B_MN && EPI == EPI_ACCUM) {
+          wg3 = (flags & F_WG3) != 0;
+          if (wg3 && c >= 6) {  // only three 64-column accumulators are live
+            if (c == my_last && has_acc) {
+              ptx::tc_fence_before();
+              if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+            }
+            continue;
+          }
+        }
         uint4 rcur[4] = {};
         bool rcur_ok = false;
         if constexpr (EPI == EPI_RESID) {
@@ -574,6 +666,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         cx.ncol0 = n0 + c * 32;
         cx.dcol = dcol0 + c * 32;
         cx.drow = drow; cx.rrow = rrow; cx.ztap = ztap; cx.row_in = row_in; cx.row_valid = row_valid;
+        if (wg3) {  // accumulator c / 2 is tap 3 * ztap + c / 2; its two chunks are input channels 0-31 / 32-63
+          cx.ztap = 3 * ztap + (c >> 1);
+          cx.ncol0 = (c & 1) * 32;
+          cx.dcol = cx.ztap * p.d_tap_n + cx.ncol0;
+        }
         float* st0 = &s_stats[tcount & 1][wq][0][c * 32];
         float* st1 = &s_stats[tcount & 1][wq][1][c * 32];
         if (cx.ncol0 >= ncols) {
@@ -713,7 +810,7 @@ static void plan_split_k(const cris_gemm_args* a, int* bn_out, int* splits_out) 
 }
 
 template <int BN, int BK, bool A_MN, bool B_MN, int EPI>
-static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream) {
+static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t stream, unsigned extra_flags = 0) {
   using Cfg = TileCfg<BN, BK>;
   CUtensorMap tmA, tmB;
   const long long bin = a->batch_inner > 1 ? a->batch_inner : 1;
@@ -734,8 +831,8 @@ static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream
   else
     b_inner = (a->tap_mode == CRIS_TAP_ACCUM && a->b_tap_k > 0) ? (long long)(a->taps - 1) * a->b_tap_k + a->K : a->K;
   if (B_MN)
-    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, bin, a->strideB2, 64, BK,
-                   CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, bin, a->strideB2, 64,
+                   (extra_flags & F_WG3) ? BK + 2 : BK, CU_TENSOR_MAP_SWIZZLE_128B);
   else
     rc = make_tmap(&tmB, a->B, b_inner, b_rows, a->ldb, a->batch, a->strideB, bin, a->strideB2, BK, BN,
                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
@@ -784,7 +881,7 @@ static int launch_tc_epi(const cris_gemm_args* a, const GemmKArgs& k, cudaStream
     kk.flags = (a->bias ? F_BIAS : 0) | (a->act == CRIS_ACT_RELU ? F_RELU : 0) |
                (a->act == CRIS_ACT_RELU_POST ? F_RELU_POST : 0) | (fast ? F_FAST : 0) |
                (kk.tma_store ? F_TMA : 0) | (a->d_fp32 ? F_DFP32 : 0) | (a->colstats ? F_STATS : 0) |
-               (a->tap_mode == CRIS_TAP_WGRAD ? F_WGRAD : 0) | (a->alpha != 1.0f ? F_ALPHA : 0);
+               (a->tap_mode == CRIS_TAP_WGRAD ? F_WGRAD : 0) | (a->alpha != 1.0f ? F_ALPHA : 0) | extra_flags;
   }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, kk, tiles_n, tiles_m, (int)total);
   CRIS_LAUNCH_OK();
@@ -805,6 +902,14 @@ static int launch_tc(const cris_gemm_args* a, const GemmKArgs& k, cudaStream_t s
 }
 
 static long long* g_trace = nullptr;  // debug timeline buffer (cris_debug_set_trace)
+
+static bool wg3_enabled() {  // CRIS_B200_WGRAD3=0 selects the tap-per-unit wgrad for small-channel 3x3 layers
+  static const bool on = [] {
+    const char* e = getenv("CRIS_B200_WGRAD3");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 
 int gemm_dispatch(const cris_gemm_args* a_in, cudaStream_t stream) {
   CRIS_CHECK_ARG(a_in != nullptr, "null gemm args");
@@ -844,6 +949,23 @@ int gemm_dispatch(const cris_gemm_args* a_in, cudaStream_t stream) {
   k.trace = g_trace;
 
   const bool amn = a->a_mn != 0, bmn = a->b_mn != 0;
+  if (a->tap_mode == CRIS_TAP_WGRAD && a->taps == 9 && amn && bmn && a->accumulate && a->d_fp32 && a->N <= 64 &&
+      a->batch == 1 && a->d_col_stride <= 1 && wg3_enabled()) {
+    bool rows_ok = true;  // tap index = 3 * (dy + 1) + (dx + 1): the taps of one kernel row are consecutive x rows
+    for (int g = 0; g < 3; ++g)
+      rows_ok = rows_ok && a->tap_off[3 * g + 1] == a->tap_off[3 * g] + 1 && a->tap_off[3 * g + 2] == a->tap_off[3 * g] + 2;
+    if (rows_ok) {
+      k.taps_z = 3;
+      if (a_in->splits == 0) {  // automatic plan: two waves of (M tiles x 3 kernel rows x splits) units
+        const long long tiles = (long long)((a->M + BM - 1) / BM) * 3;
+        const int nkb = (a->K + 63) / 64;
+        long long sp = tiles >= 2 * num_sms() ? 1 : (2 * num_sms()) / tiles;
+        if (sp > nkb / 4) sp = nkb / 4;
+        k.splits = sp < 1 ? 1 : (int)sp;
+      }
+      return launch_tc_epi<256, 64, true, true, EPI_ACCUM>(a, k, stream, F_WG3);
+    }
+  }
   const bool k32 = (a->K <= 32) && !amn && !bmn;  // stem convs: 32 input channels per tap
   if (k32) {
     if (a->N <= 32) return launch_tc<32, 32, false, false>(a, k, stream);

@@ -379,6 +379,8 @@ static void perf(int only = -1) {
       {"wgrad3x3 64x64 64x(106x106)", 64, 64, 64 * 106 * 106, 9, 106, 106, 1, 1},
       {"wgrad1x1 2048x512 64x(15x15)", 2048, 512, 64 * 15 * 15, 1, 0, 0, 1, 1},
       {"dgrad3x3 64x(106x106) 256->512", 64 * 106 * 106, 512, 256, 9, 106, 106, 0, 1},
+      {"wgrad3x3 32x32 64x(210x210)", 32, 32, 64 * 210 * 210, 9, 210, 210, 1, 1},
+      {"wgrad3x3 64x32 64x(210x210)", 64, 32, 64 * 210 * 210, 9, 210, 210, 1, 1},
   };
   int pi = -1;
   for (const P& q : ps) {

@@ -83,6 +83,13 @@ except Exception as e: print('   parse error', e)
       CRIS_SWEEP="CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=1000,CRIS_B200_WGRAD_STREAM=0,CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=64,CRIS_B200_WGRAD_STREAM=0+CRIS_X=1,CRIS_B200_WGRAD_STREAM=1+CRIS_B200_WGRAD_JOIN=1000+CRIS_X=1" \
         timeout 600 python tools/flag_sweep.py 64 > gpurun_out/${TAG}_wgstream_sweep.log 2>&1
       echo "[wgstream sweep] rc=$?"; cat gpurun_out/${TAG}_wgstream_sweep.log | tail -8 ;;
+    wg3)
+      timeout 300 python -m pytest tests/test_gemm_native_gpu.py tests/test_ops_gpu.py -k "native or conv_bn or halo or deterministic" -q --no-header -p no:cacheprovider -rA \
+        > gpurun_out/${TAG}_tests_wg3.log 2>&1
+      echo "[tests_wg3] rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|assert|Error|MISMATCH|FAIL" gpurun_out/${TAG}_tests_wg3.log | tail -12
+      for i in 13 16 17; do
+        for f in 1 0; do echo "WGRAD3=$f"; CRIS_B200_WGRAD3=$f timeout 100 tests/native/gemm_selftest perf $i 2>&1 | grep PERF; done
+      done ;;
     tests_optim)
       timeout 300 python -m pytest tests/test_optim_gpu.py tests/test_syncbn_equiv_gpu.py -q --no-header -p no:cacheprovider -rA > gpurun_out/${TAG}_tests_optim.log 2>&1
       echo "[tests_optim] rc=$?"; grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_tests_optim.log | tail -8 ;;
