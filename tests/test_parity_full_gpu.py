@@ -11,8 +11,10 @@ Stated tolerances (bf16 storage / tensor-core operands with fp32 accumulation vs
   eval logits  rel L2 <= 3e-2; a mask pixel may differ only if its reference logit is within 0.05 of the threshold
   train loss   |delta| <= 3e-2 (batch-statistics BatchNorm amplifies storage noise; see oracle/synth.py)
   gradients    per block (norm of the block's gradient, cosine of its concatenated samples vs the reference):
-                 image tower (stem, layer1-4, attnpool): norm ratio in [0.9, 1.1], cosine >= 0.62
-                 text tower, neck, decoder, projector  : norm ratio in [0.9, 1.1], cosine >= 0.92
+                 image tower (stem, layer1-4, attnpool): norm ratio in [0.9, 1.1], cosine >= 0.55
+                 text tower, neck, decoder, projector  : norm ratio in [0.9, 1.1], cosine >= 0.88
+               (floors sit below the spread of five full runs on different boxes: image-tower blocks 0.67-0.91, worst
+               r101 layer2 0.675 / 0.706 / 0.727 / 0.746 / 0.807; r101 text blocks 0-5 0.940-0.971; neck 0.93-0.98)
                per parameter: norm ratio in [0.8, 1.25] for >= 97 % of the tensors
                Measured (round 2, gpurun_out/parity_*.json): r50 B=8 every tensor within [0.87, 1.12], head / text /
                neck cosines 0.98-1.00, image-tower cosines 0.80-0.90 (r101, 101 layers deep: 0.68-0.79).  That is the
@@ -105,7 +107,7 @@ def check_against_golden(arch, tag, golden_dir, B):
     assert rep["running_stat_norm_err_max"] <= 5e-2
     for name, G in groups.items():
         assert 0.9 <= G["norm_ratio"] <= 1.1, (name, G)
-        floor = 0.62 if _is_image_tower(name) else 0.92
+        floor = 0.55 if _is_image_tower(name) else 0.88
         assert G["cos"] >= floor, (name, G, floor)
     assert rep["param_outlier_fraction"] <= PARAM_OUTLIERS, rep["worst10"]
     return rep
